@@ -1,0 +1,736 @@
+// C-ABI of groundgrid_b200 (include/groundgrid_b200.h): handle management, device arena,
+// parameter staging, stream pipeline.  All compute happens in gg_kernels.cu; there is no CPU
+// fallback -- without a usable sm_100 device every compute call returns GG_E_CUDA.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gg_host.h"
+#include "gg_internal.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define GG_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) return fail(GG_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int kStreams = 4;
+constexpr int kRing = 16;
+
+// CUDA-event pairs around every kernel launch while profiling is enabled.
+struct EventProfiler : gg::Profiler {
+    struct Rec {
+        int id;
+        cudaEvent_t a, b;
+    };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    size_t dropped = 0;
+    static constexpr size_t kMaxRecs = 16384;
+    cudaEvent_t get() {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void begin(int id, cudaStream_t st) override {
+        if (recs.size() >= kMaxRecs) {
+            ++dropped;
+            cur = nullptr;
+            return;
+        }
+        recs.push_back({id, get(), get()});
+        cur = &recs.back();
+        cudaEventRecord(cur->a, st);
+    }
+    void end(int, cudaStream_t st) override {
+        if (cur) cudaEventRecord(cur->b, st);
+        cur = nullptr;
+    }
+    // after the streams were synchronised
+    void collect(double* ms, uint32_t* count) {
+        for (Rec& r : recs) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+                ms[r.id] += t;
+                count[r.id] += 1;
+            }
+            pool.push_back(r.a);
+            pool.push_back(r.b);
+        }
+        recs.clear();
+    }
+    ~EventProfiler() override {
+        for (Rec& r : recs) {
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+        for (cudaEvent_t e : pool) cudaEventDestroy(e);
+    }
+    Rec* cur = nullptr;
+};
+
+struct SlotState {
+    bool have_map = false;
+    double px = 0.0, py = 0.0;
+    size_t n_points = 0;       // points of the resident / last scan
+    int last_stop = 0;         // stop_after of the last run (decides what "points" names)
+    bool ran = false;
+    bool output_valid = false;
+    const gg_point* src = nullptr;  // caller-owned device cloud of the last scan (null: the slot's own buffer)
+};
+
+}  // namespace
+
+struct gg_handle_s {
+    int device = 0;
+    int n_slots = 0;
+    size_t pcap = 0;
+    unsigned flags = 0;
+    double dimension_m = 0.0;
+    float resolution = 0.f;
+    gg_config cfg{};
+    gg::View view{};
+    std::vector<SlotState> slots;
+    cudaStream_t streams[kStreams] = {};
+    bool own_streams = true;
+    int n_streams = kStreams;
+    // parameter staging ring: pinned host copy + device copy per entry
+    gg::SlotParams* h_ring = nullptr;
+    gg::SlotParams* d_ring = nullptr;
+    cudaEvent_t ring_ev[kRing] = {};
+    bool ring_used[kRing] = {};
+    int ring_pos = 0;
+    uint64_t launches = 0;
+    std::vector<void*> dev_allocs;
+    int sched_levels = 0, sched_visits = 0, sched_max = 0;
+    bool out_cloud_ready = false;
+    EventProfiler* prof = nullptr;   // non-null while profiling is enabled
+    double prof_ms[gg::K_NUM] = {};
+    uint32_t prof_count[gg::K_NUM] = {};
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(gg_handle h, T** p, size_t count) {
+    void* q = nullptr;
+    GG_CUDA(cudaMalloc(&q, count * sizeof(T) + 256));
+    h->dev_allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return GG_OK;
+}
+
+int check_slot(gg_handle h, int slot) {
+    if (!h) return fail(GG_E_ARG, "null handle");
+    if (slot < 0 || slot >= h->n_slots) return fail(GG_E_ARG, "slot %d out of range [0, %d)", slot, h->n_slots);
+    return GG_OK;
+}
+
+int layer_index(gg_handle h, int slot, const char* name, int* idx) {
+    struct Entry {
+        const char* name;
+        int idx;
+        bool full_only;
+    };
+    static const Entry table[] = {
+        {"ground", gg::L_GROUND, false},        {"groundpatch", gg::L_GROUNDPATCH, false},
+        {"variance", gg::L_VARIANCE, false},    {"minGroundHeight", gg::L_MINH, false},
+        {"maxGroundHeight", gg::L_MAXH, true},  {"groundCandidates", gg::L_GCAND, true},
+        {"planeDist", gg::L_PLANEDIST, true},   {"m2", gg::L_M2, true},
+        {"meanVariance", gg::L_MEAN, true},     {"pointsRaw", gg::L_RAW, true},
+        {"count", gg::L_COUNT, false},          {"obstacles", gg::L_OBSTACLES, false},
+    };
+    if (!name) return fail(GG_E_ARG, "null layer name");
+    if (std::strcmp(name, "points") == 0) {
+        // the reference reuses "points": kept-point count while rasterising (:309), non-ground
+        // point count after the label loop (:147,176)
+        const SlotState& s = h->slots[slot];
+        *idx = (s.ran && s.last_stop != 0) ? gg::L_COUNT : gg::L_OBSTACLES;
+        return GG_OK;
+    }
+    for (const Entry& e : table)
+        if (std::strcmp(name, e.name) == 0) {
+            if (e.full_only && !(h->flags & GG_FLAG_FULL_LAYERS)) return fail(GG_E_LAYER, "layer '%s' needs GG_FLAG_FULL_LAYERS", name);
+            *idx = e.idx;
+            return GG_OK;
+        }
+    return fail(GG_E_LAYER, "unknown layer '%s'", name);
+}
+
+// Reserve the next staging entry (waits only if the ring wrapped onto an in-flight entry).
+int ring_acquire(gg_handle h, gg::SlotParams** host, gg::SlotParams** dev, int* pos) {
+    const int p = h->ring_pos;
+    h->ring_pos = (p + 1) % kRing;
+    if (h->ring_used[p]) GG_CUDA(cudaEventSynchronize(h->ring_ev[p]));
+    *host = h->h_ring + (size_t)p * h->n_slots;
+    *dev = h->d_ring + (size_t)p * h->n_slots;
+    *pos = p;
+    return GG_OK;
+}
+
+int ring_commit(gg_handle h, int pos, int count, cudaStream_t st) {
+    gg::SlotParams* host = h->h_ring + (size_t)pos * h->n_slots;
+    gg::SlotParams* dev = h->d_ring + (size_t)pos * h->n_slots;
+    GG_CUDA(cudaMemcpyAsync(dev, host, (size_t)count * sizeof(gg::SlotParams), cudaMemcpyHostToDevice, st));
+    GG_CUDA(cudaEventRecord(h->ring_ev[pos], st));
+    h->ring_used[pos] = true;
+    return GG_OK;
+}
+
+void fill_params(gg_handle h, const gg_scan_desc& d, gg::SlotParams& p, const gg_point* src) {
+    const SlotState& s = h->slots[d.slot];
+    std::memset(&p, 0, sizeof(p));
+    p.px = s.px;
+    p.py = s.py;
+    p.ox = d.origin[0];
+    p.oy = d.origin[1];
+    p.oz = d.origin[2];
+    p.base_z_f = (float)d.base_z;  // ggl(c, c) = ps.point.z (double -> float), GroundSegmentation.cpp:411
+    p.n_points = (int)d.n_points;
+    p.slot = d.slot;
+    p.src = src ? src : h->view.points + (size_t)d.slot * h->pcap;
+}
+
+// enqueue the kernels of `count` scans on stream `st`
+int run_scans_on(gg_handle h, int count, const gg_scan_desc* scans, int stop_after, cudaStream_t st,
+                 const gg_point* const* dev_points = nullptr) {
+    if (count <= 0) return GG_OK;
+    if (count > h->n_slots) return fail(GG_E_ARG, "count %d exceeds the number of slots %d", count, h->n_slots);
+    gg::SlotParams *hp = nullptr, *dp = nullptr;
+    int pos = 0;
+    int rc = ring_acquire(h, &hp, &dp, &pos);
+    if (rc) return rc;
+    int max_points = 0;
+    for (int i = 0; i < count; ++i) {
+        const gg_scan_desc& d = scans[i];
+        if ((rc = check_slot(h, d.slot))) return rc;
+        if (!h->slots[d.slot].have_map) return fail(GG_E_STATE, "slot %d: map not initialised", d.slot);
+        if (d.n_points > h->pcap) return fail(GG_E_ARG, "slot %d: %zu points exceed capacity %zu", d.slot, d.n_points, h->pcap);
+        fill_params(h, d, hp[i], dev_points ? dev_points[i] : nullptr);
+        max_points = std::max(max_points, (int)d.n_points);
+        SlotState& s = h->slots[d.slot];
+        s.n_points = d.n_points;
+        s.last_stop = stop_after;
+        s.ran = true;
+        s.output_valid = false;
+        s.src = dev_points ? dev_points[i] : nullptr;
+    }
+    if ((rc = ring_commit(h, pos, count, st))) return rc;
+    h->launches += gg::launch_scan_pipeline(h->view, dp, count, max_points, stop_after, st, h->prof);
+    GG_CUDA(cudaGetLastError());
+    return GG_OK;
+}
+
+int ensure_out_cloud(gg_handle h) {
+    if (h->out_cloud_ready) return GG_OK;
+    int rc = dev_alloc(h, &h->view.out_cloud, (size_t)h->n_slots * h->pcap);
+    if (rc) return rc;
+    h->out_cloud_ready = true;
+    return GG_OK;
+}
+
+int run_output_on(gg_handle h, int slot, bool want_cloud, cudaStream_t st) {
+    SlotState& s = h->slots[slot];
+    if (!s.ran || s.last_stop != 0) return fail(GG_E_STATE, "slot %d: no completed scan", slot);
+    int rc;
+    if (want_cloud && (rc = ensure_out_cloud(h))) return rc;
+    gg::SlotParams *hp = nullptr, *dp = nullptr;
+    int pos = 0;
+    if ((rc = ring_acquire(h, &hp, &dp, &pos))) return rc;
+    std::memset(&hp[0], 0, sizeof(gg::SlotParams));
+    hp[0].slot = slot;
+    hp[0].n_points = (int)s.n_points;
+    hp[0].src = s.src ? s.src : h->view.points + (size_t)slot * h->pcap;
+    if ((rc = ring_commit(h, pos, 1, st))) return rc;
+    h->launches += gg::launch_output(h->view, dp, 1, (int)s.n_points, want_cloud, st, h->prof);
+    GG_CUDA(cudaGetLastError());
+    s.output_valid = true;
+    return GG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void gg_default_config(gg_config* c) {
+    if (!c) return;
+    c->point_count_cell_variance_threshold = 10;
+    c->max_ring = 1024;
+    c->groundpatch_detection_minimum_threshold = 0.01;
+    c->distance_factor = 0.0001;
+    c->minimum_distance_factor = 0.0005;
+    c->miminum_point_height_threshold = 0.3;
+    c->minimum_point_height_obstacle_threshold = 0.1;
+    c->outlier_tolerance = 0.1;
+    c->ground_patch_detection_minimum_point_count_threshold = 0.25;
+    c->patch_size_change_distance = 20.0;
+    c->occupied_cells_decrease_factor = 5.0;
+    c->occupied_cells_point_count_factor = 20.0;
+    c->min_outlier_detection_ground_confidence = 1.25;
+    c->thread_count = 8;
+}
+
+const char* gg_last_error(void) { return g_last_error.c_str(); }
+
+int gg_create(double dimension_m, float resolution, int device, int n_slots, size_t max_points, unsigned flags, void* stream,
+              gg_handle* out) {
+    if (!out) return fail(GG_E_ARG, "null out pointer");
+    *out = nullptr;
+    if (n_slots <= 0 || max_points == 0 || !(resolution > 0.f) || !(dimension_m > 0.0)) return fail(GG_E_ARG, "bad geometry / sizes");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(GG_E_CUDA, "no CUDA device available (groundgrid_b200 has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(GG_E_ARG, "device %d out of range", device);
+    cudaDeviceProp prop;
+    GG_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(GG_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    GG_CUDA(cudaSetDevice(device));
+
+    const int n = gg::cells_per_side(dimension_m, resolution);
+    if (n < 8 || n > 4096) return fail(GG_E_ARG, "unsupported map size %d cells", n);
+
+    gg_handle h = new gg_handle_s();
+    h->device = device;
+    h->n_slots = n_slots;
+    h->pcap = (max_points + 255) / 256 * 256;
+    h->flags = flags;
+    h->dimension_m = dimension_m;
+    h->resolution = resolution;
+    gg_default_config(&h->cfg);
+    h->slots.resize(n_slots);
+    gg::View& v = h->view;
+    gg::derive_constants(h->cfg, dimension_m, resolution, flags, v.k);
+    if (v.k.N != n) {
+        delete h;
+        return fail(GG_E_ARG, "cell count mismatch between init (%d) and setGeometry (%d)", n, v.k.N);
+    }
+    const size_t N2 = (size_t)v.k.N2;
+    v.n_layers = (flags & GG_FLAG_FULL_LAYERS) ? gg::L_NUM : gg::L_NUM_LIVE;
+    v.pcap = h->pcap;
+    v.sort_blocks = (int)((h->pcap + gg::SORT_TILE - 1) / gg::SORT_TILE);
+    v.out_blocks = (int)((h->pcap + gg::OUT_TILE - 1) / gg::OUT_TILE);
+    int bits = 1;
+    while ((1u << bits) < (unsigned)(N2 + 1)) ++bits;  // keys are cell ids in [0, N2] (N2 = "not rasterised")
+    v.key_bits = bits;
+    v.bits_lo = (bits + 1) / 2;
+    v.bits_hi = bits - v.bits_lo;
+    const int bits_max = std::max(v.bits_lo, v.bits_hi);
+
+#define GG_TRY(expr)            \
+    do {                        \
+        int rc__ = (expr);      \
+        if (rc__) {             \
+            gg_destroy(h);      \
+            return rc__;        \
+        }                       \
+    } while (0)
+#define GG_CUDA_TRY(call)                                                                             \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess) {                                                                     \
+            gg_destroy(h);                                                                            \
+            return fail(GG_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                             \
+    } while (0)
+
+    const size_t S = (size_t)n_slots, P = h->pcap;
+    GG_TRY(dev_alloc(h, &v.layers, S * v.n_layers * N2));
+    float* expected = nullptr;
+    GG_TRY(dev_alloc(h, &expected, N2));
+    v.expected = expected;
+    GG_TRY(dev_alloc(h, &v.points, S * P));
+    GG_TRY(dev_alloc(h, &v.key, S * P));
+    GG_TRY(dev_alloc(h, &v.key2, S * P));
+    GG_TRY(dev_alloc(h, &v.zval, S * P));
+    GG_TRY(dev_alloc(h, &v.z2, S * P));
+    GG_TRY(dev_alloc(h, &v.zsorted, S * P));
+    GG_TRY(dev_alloc(h, &v.dist, S * P));
+    GG_TRY(dev_alloc(h, &v.code, S * P));
+    GG_TRY(dev_alloc(h, &v.labels, S * P));
+    GG_TRY(dev_alloc(h, &v.cnt_i, S * N2));
+    GG_TRY(dev_alloc(h, &v.raw_i, (flags & GG_FLAG_FULL_LAYERS) ? S * N2 : 1));
+    GG_TRY(dev_alloc(h, &v.cellstart, S * N2));
+    GG_TRY(dev_alloc(h, &v.sort_hist, S * ((size_t)v.sort_blocks << bits_max)));
+    GG_TRY(dev_alloc(h, &v.out_index, S * P));
+    GG_TRY(dev_alloc(h, &v.out_counts, S * (3 * (size_t)v.out_blocks + 1)));
+    GG_TRY(dev_alloc(h, &v.roll_scratch, S * 2 * N2));
+    v.out_cloud = nullptr;
+    GG_CUDA_TRY(cudaMemset(v.layers, 0, S * v.n_layers * N2 * sizeof(float)));
+
+    // expectedPoints table (host libm, like the reference) and the spiral wavefront schedule
+    {
+        std::vector<float> table;
+        gg::build_expected_points(n, table);
+        GG_CUDA_TRY(cudaMemcpy(expected, table.data(), N2 * sizeof(float), cudaMemcpyHostToDevice));
+        std::vector<int> ls;
+        std::vector<uint32_t> vs;
+        gg::build_spiral_schedule(n, ls, vs);
+        int* d_ls = nullptr;
+        uint32_t* d_vs = nullptr;
+        GG_TRY(dev_alloc(h, &d_ls, ls.size()));
+        GG_TRY(dev_alloc(h, &d_vs, vs.size() + 1));
+        GG_CUDA_TRY(cudaMemcpy(d_ls, ls.data(), ls.size() * sizeof(int), cudaMemcpyHostToDevice));
+        GG_CUDA_TRY(cudaMemcpy(d_vs, vs.data(), vs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        v.level_start = d_ls;
+        v.visits = d_vs;
+        v.levels = (int)ls.size() - 1;
+        h->sched_levels = v.levels;
+        h->sched_visits = (int)vs.size();
+        for (size_t l = 0; l + 1 < ls.size(); ++l) h->sched_max = std::max(h->sched_max, ls[l + 1] - ls[l]);
+    }
+
+    if (stream) {
+        h->own_streams = false;
+        h->n_streams = 1;
+        h->streams[0] = static_cast<cudaStream_t>(stream);
+    } else {
+        for (int i = 0; i < kStreams; ++i) GG_CUDA_TRY(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+    }
+    GG_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h->h_ring), sizeof(gg::SlotParams) * kRing * S, cudaHostAllocDefault));
+    GG_TRY(dev_alloc(h, &h->d_ring, (size_t)kRing * S));
+    for (int i = 0; i < kRing; ++i) GG_CUDA_TRY(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
+#undef GG_TRY
+#undef GG_CUDA_TRY
+    *out = h;
+    return GG_OK;
+}
+
+int gg_destroy(gg_handle h) {
+    if (!h) return GG_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    delete h->prof;
+    for (void* p : h->dev_allocs) cudaFree(p);
+    if (h->h_ring) cudaFreeHost(h->h_ring);
+    for (int i = 0; i < kRing; ++i)
+        if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
+    if (h->own_streams)
+        for (int i = 0; i < kStreams; ++i)
+            if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+    delete h;
+    return GG_OK;
+}
+
+int gg_cells_per_side(gg_handle h) { return h ? h->view.k.N : GG_E_ARG; }
+int gg_num_slots(gg_handle h) { return h ? h->n_slots : GG_E_ARG; }
+void* gg_stream(gg_handle h) { return h ? h->streams[0] : nullptr; }
+uint64_t gg_kernel_launches(gg_handle h) { return h ? h->launches : 0; }
+
+int gg_spiral_schedule_info(gg_handle h, int* levels, int* visits, int* max_per_level) {
+    if (!h) return fail(GG_E_ARG, "null handle");
+    if (levels) *levels = h->sched_levels;
+    if (visits) *visits = h->sched_visits;
+    if (max_per_level) *max_per_level = h->sched_max;
+    return GG_OK;
+}
+
+int gg_set_config(gg_handle h, const gg_config* cfg) {
+    if (!h || !cfg) return fail(GG_E_ARG, "null argument");
+    h->cfg = *cfg;
+    gg::derive_constants(h->cfg, h->dimension_m, h->resolution, h->flags, h->view.k);  // by-value kernel argument: applies to the next launch
+    return GG_OK;
+}
+
+int gg_get_config(gg_handle h, gg_config* cfg) {
+    if (!h || !cfg) return fail(GG_E_ARG, "null argument");
+    *cfg = h->cfg;
+    return GG_OK;
+}
+
+int gg_init_map(gg_handle h, int slot, double x, double y, double z) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    GG_CUDA(cudaSetDevice(h->device));
+    SlotState& s = h->slots[slot];
+    s = SlotState();
+    s.px = x;
+    s.py = y;
+    s.have_map = true;
+    h->launches += gg::launch_init_map(h->view, slot, (float)z, h->streams[0]);
+    GG_CUDA(cudaGetLastError());
+    return GG_OK;
+}
+
+int gg_update_pose_batch(gg_handle h, int count, const int* slots, const double* xy, const double* T, int* moved) {
+    if (!h || !slots || !xy || !T) return fail(GG_E_ARG, "null argument");
+    if (count <= 0) return GG_OK;
+    if (count > h->n_slots) return fail(GG_E_ARG, "count exceeds slots");
+    GG_CUDA(cudaSetDevice(h->device));
+    gg::SlotParams *hp = nullptr, *dp = nullptr;
+    int pos = 0, rc;
+    if ((rc = ring_acquire(h, &hp, &dp, &pos))) return rc;
+    int any = 0;
+    for (int i = 0; i < count; ++i) {
+        if ((rc = check_slot(h, slots[i]))) return rc;
+        SlotState& s = h->slots[slots[i]];
+        if (!s.have_map) return fail(GG_E_STATE, "slot %d: map not initialised", slots[i]);
+        gg::SlotParams& p = hp[i];
+        std::memset(&p, 0, sizeof(p));
+        gg::move_map(h->view.k.res, s.px, s.py, xy[2 * i], xy[2 * i + 1], p.shift_i, p.shift_j);
+        p.px = s.px;
+        p.py = s.py;
+        const double* t = T + 12 * (size_t)i;
+        p.t20 = t[8];
+        p.t21 = t[9];
+        p.t22 = t[10];
+        p.t23 = t[11];
+        p.slot = slots[i];
+        const int m = (p.shift_i != 0 || p.shift_j != 0) ? 1 : 0;
+        if (moved) moved[i] = m;
+        any |= m;
+    }
+    if (!any) return GG_OK;  // "We havent moved so we have nothing to do", GroundGrid.cpp:136-137
+    if ((rc = ring_commit(h, pos, count, h->streams[0]))) return rc;
+    h->launches += gg::launch_roll(h->view, dp, count, h->streams[0], h->prof);
+    GG_CUDA(cudaGetLastError());
+    return GG_OK;
+}
+
+int gg_update_pose(gg_handle h, int slot, double x, double y, const double T[12], int* moved) {
+    const double xy[2] = {x, y};
+    return gg_update_pose_batch(h, 1, &slot, xy, T, moved);
+}
+
+int gg_get_map_position(gg_handle h, int slot, double xy[2]) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    if (!xy) return fail(GG_E_ARG, "null argument");
+    xy[0] = h->slots[slot].px;
+    xy[1] = h->slots[slot].py;
+    return GG_OK;
+}
+
+int gg_set_map_position(gg_handle h, int slot, double x, double y) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    h->slots[slot].px = x;
+    h->slots[slot].py = y;
+    return GG_OK;
+}
+
+int gg_upload_points(gg_handle h, int slot, const gg_point* points, size_t n) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    if (n > h->pcap) return fail(GG_E_ARG, "%zu points exceed capacity %zu", n, h->pcap);
+    if (n && !points) return fail(GG_E_ARG, "null points");
+    GG_CUDA(cudaSetDevice(h->device));
+    if (n) GG_CUDA(cudaMemcpyAsync(h->view.points + (size_t)slot * h->pcap, points, n * sizeof(gg_point), cudaMemcpyHostToDevice, h->streams[0]));
+    h->slots[slot].n_points = n;
+    return GG_OK;
+}
+
+int gg_run_scans(gg_handle h, int count, const gg_scan_desc* scans, int stop_after) {
+    if (!h || !scans) return fail(GG_E_ARG, "null argument");
+    if (stop_after < 0 || stop_after > 3) return fail(GG_E_ARG, "stop_after must be 0..3");
+    GG_CUDA(cudaSetDevice(h->device));
+    return run_scans_on(h, count, scans, stop_after, h->streams[0]);
+}
+
+int gg_run_scans_device(gg_handle h, int count, const gg_scan_desc* scans, const gg_point* const* dev_points, int stop_after) {
+    if (!h || !scans || !dev_points) return fail(GG_E_ARG, "null argument");
+    if (stop_after < 0 || stop_after > 3) return fail(GG_E_ARG, "stop_after must be 0..3");
+    for (int i = 0; i < count; ++i)
+        if (!dev_points[i] && scans[i].n_points) return fail(GG_E_ARG, "scan %d: null device cloud", i);
+    GG_CUDA(cudaSetDevice(h->device));
+    return run_scans_on(h, count, scans, stop_after, h->streams[0], dev_points);
+}
+
+int gg_profile_enable(gg_handle h, int on) {
+    if (!h) return fail(GG_E_ARG, "null handle");
+    GG_CUDA(cudaSetDevice(h->device));
+    if (on && !h->prof) h->prof = new EventProfiler();
+    if (!on && h->prof) {
+        int rc = gg_synchronize(h);
+        if (rc) return rc;
+        h->prof->collect(h->prof_ms, h->prof_count);
+        delete h->prof;
+        h->prof = nullptr;
+    }
+    return GG_OK;
+}
+
+int gg_profile_read(gg_handle h, double* ms_per_kernel, uint32_t* launches_per_kernel, int reset) {
+    if (!h) return fail(GG_E_ARG, "null handle");
+    int rc = gg_synchronize(h);
+    if (rc) return rc;
+    if (h->prof) h->prof->collect(h->prof_ms, h->prof_count);
+    for (int k = 0; k < gg::K_NUM; ++k) {
+        if (ms_per_kernel) ms_per_kernel[k] = h->prof_ms[k];
+        if (launches_per_kernel) launches_per_kernel[k] = h->prof_count[k];
+        if (reset) {
+            h->prof_ms[k] = 0.0;
+            h->prof_count[k] = 0;
+        }
+    }
+    return GG_OK;
+}
+
+int gg_profile_kernel_count(void) { return gg::K_NUM; }
+
+const char* gg_profile_kernel_name(int id) {
+    static const char* names[gg::K_NUM] = {"k_clear_scan",  "k_rasterize",     "k_sort_hist(lo)", "k_sort_scan(lo)", "k_sort_scatter(lo)",
+                                           "k_sort_hist(hi)", "k_sort_scan(hi)", "k_sort_scatter(hi)", "k_scan_cells", "k_cell_stats",
+                                           "k_detect",      "k_spiral",        "k_label",         "k_roll_gather",   "k_roll_commit",
+                                           "k_out_count",   "k_out_scan",      "k_out_write"};
+    return (id >= 0 && id < gg::K_NUM) ? names[id] : "";
+}
+
+int gg_download_labels(gg_handle h, int slot, uint8_t* labels_out, size_t n) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    if (n > h->pcap || (n && !labels_out)) return fail(GG_E_ARG, "bad label buffer");
+    GG_CUDA(cudaSetDevice(h->device));
+    if (n) GG_CUDA(cudaMemcpyAsync(labels_out, h->view.labels + (size_t)slot * h->pcap, n, cudaMemcpyDeviceToHost, h->streams[0]));
+    return GG_OK;
+}
+
+int gg_synchronize(gg_handle h) {
+    if (!h) return fail(GG_E_ARG, "null handle");
+    GG_CUDA(cudaSetDevice(h->device));
+    for (int i = 0; i < h->n_streams; ++i) GG_CUDA(cudaStreamSynchronize(h->streams[i]));
+    return GG_OK;
+}
+
+int gg_get_output(gg_handle h, int slot, uint32_t* index_out, gg_point* cloud_out, size_t* n_out) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    GG_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->streams[0];
+    if ((rc = run_output_on(h, slot, cloud_out != nullptr, st))) return rc;
+    int total = 0;
+    const gg::View& v = h->view;
+    GG_CUDA(cudaMemcpyAsync(&total, v.out_counts + (size_t)slot * (3 * v.out_blocks + 1) + 3 * v.out_blocks, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GG_CUDA(cudaStreamSynchronize(st));
+    if (n_out) *n_out = (size_t)total;
+    if (index_out && total) GG_CUDA(cudaMemcpyAsync(index_out, v.out_index + (size_t)slot * h->pcap, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (cloud_out && total) GG_CUDA(cudaMemcpyAsync(cloud_out, v.out_cloud + (size_t)slot * h->pcap, (size_t)total * sizeof(gg_point), cudaMemcpyDeviceToHost, st));
+    GG_CUDA(cudaStreamSynchronize(st));
+    return GG_OK;
+}
+
+int gg_filter_cloud(gg_handle h, int slot, const gg_point* points, size_t n, const float origin[3], double base_z,
+                    uint8_t* labels_out, uint32_t* index_out, gg_point* cloud_out, size_t* n_out) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    if (!origin) return fail(GG_E_ARG, "null origin");
+    if (!h->slots[slot].have_map) return fail(GG_E_STATE, "slot %d: map not initialised", slot);
+    if ((rc = gg_upload_points(h, slot, points, n))) return rc;
+    gg_scan_desc d;
+    std::memset(&d, 0, sizeof(d));
+    d.slot = slot;
+    d.n_points = n;
+    d.origin[0] = origin[0];
+    d.origin[1] = origin[1];
+    d.origin[2] = origin[2];
+    d.base_z = base_z;
+    if ((rc = run_scans_on(h, 1, &d, 0, h->streams[0]))) return rc;
+    if (labels_out && (rc = gg_download_labels(h, slot, labels_out, n))) return rc;
+    if (index_out || cloud_out || n_out) return gg_get_output(h, slot, index_out, cloud_out, n_out);
+    GG_CUDA(cudaStreamSynchronize(h->streams[0]));
+    return GG_OK;
+}
+
+int gg_filter_cloud_batch(gg_handle h, int count, const gg_scan_desc* scans, const gg_point* const* points, uint8_t* const* labels_out) {
+    if (!h || !scans || !points) return fail(GG_E_ARG, "null argument");
+    if (count <= 0) return GG_OK;
+    if (count > h->n_slots) return fail(GG_E_ARG, "count exceeds slots");
+    GG_CUDA(cudaSetDevice(h->device));
+    // Groups of scans travel down separate streams so that the H2D copies of one group overlap
+    // the kernels of another and the D2H of a third.  Work enqueued earlier on the primary
+    // stream (map init / roll) must be visible to all of them first.
+    const int groups = std::min(h->n_streams, count);
+    if (groups > 1) {
+        cudaEvent_t ev;
+        GG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        GG_CUDA(cudaEventRecord(ev, h->streams[0]));
+        for (int g = 1; g < groups; ++g) GG_CUDA(cudaStreamWaitEvent(h->streams[g], ev, 0));
+        GG_CUDA(cudaEventDestroy(ev));
+    }
+    const int per = (count + groups - 1) / groups;
+    for (int g = 0; g < groups; ++g) {
+        const int b = g * per, e = std::min(count, b + per);
+        if (b >= e) break;
+        cudaStream_t st = h->streams[g];
+        for (int i = b; i < e; ++i) {
+            const gg_scan_desc& d = scans[i];
+            int rc = check_slot(h, d.slot);
+            if (rc) return rc;
+            if (d.n_points > h->pcap) return fail(GG_E_ARG, "slot %d: too many points", d.slot);
+            if (d.n_points)
+                GG_CUDA(cudaMemcpyAsync(h->view.points + (size_t)d.slot * h->pcap, points[i], d.n_points * sizeof(gg_point), cudaMemcpyHostToDevice, st));
+        }
+        int rc = run_scans_on(h, e - b, scans + b, 0, st);
+        if (rc) return rc;
+        if (labels_out)
+            for (int i = b; i < e; ++i)
+                if (labels_out[i] && scans[i].n_points)
+                    GG_CUDA(cudaMemcpyAsync(labels_out[i], h->view.labels + (size_t)scans[i].slot * h->pcap, scans[i].n_points, cudaMemcpyDeviceToHost, st));
+    }
+    for (int g = 0; g < groups; ++g) GG_CUDA(cudaStreamSynchronize(h->streams[g]));
+    return GG_OK;
+}
+
+int gg_get_layer(gg_handle h, int slot, const char* name, float* dst) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    if (!dst) return fail(GG_E_ARG, "null dst");
+    GG_CUDA(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)h->view.k.N2 * sizeof(float);
+    if (name && std::strcmp(name, "expectedPoints") == 0) {
+        GG_CUDA(cudaMemcpy(dst, h->view.expected, bytes, cudaMemcpyDeviceToHost));
+        return GG_OK;
+    }
+    int idx;
+    if ((rc = layer_index(h, slot, name, &idx))) return rc;
+    if ((rc = gg_synchronize(h))) return rc;
+    GG_CUDA(cudaMemcpy(dst, h->view.layer(slot, idx), bytes, cudaMemcpyDeviceToHost));
+    return GG_OK;
+}
+
+int gg_set_layer(gg_handle h, int slot, const char* name, const float* src) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    if (!src) return fail(GG_E_ARG, "null src");
+    GG_CUDA(cudaSetDevice(h->device));
+    int idx;
+    if ((rc = layer_index(h, slot, name, &idx))) return rc;
+    if ((rc = gg_synchronize(h))) return rc;
+    GG_CUDA(cudaMemcpy(h->view.layer(slot, idx), src, (size_t)h->view.k.N2 * sizeof(float), cudaMemcpyHostToDevice));
+    return GG_OK;
+}
+
+int gg_layer_device_ptr(gg_handle h, int slot, const char* name, void** dptr) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    if (!dptr) return fail(GG_E_ARG, "null dptr");
+    int idx;
+    if ((rc = layer_index(h, slot, name, &idx))) return rc;
+    *dptr = h->view.layer(slot, idx);
+    return GG_OK;
+}
+
+}  // extern "C"

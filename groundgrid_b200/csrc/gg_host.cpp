@@ -1,0 +1,146 @@
+// Host-side (no CUDA) pieces of the library: expectedPoints table, config-derived constants,
+// the map-move arithmetic and the wavefront schedule of the spiral interpolation.  They are
+// exported with a gg_host_ prefix so the CPU test-suite can exercise them without a GPU.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "gg_host.h"
+
+namespace gg {
+
+// GroundSegmentation::init (src/GroundSegmentation.cpp:37-48).  Built on the host with the
+// platform libm (hypot / atanf), exactly like the reference, then uploaded once.
+int cells_per_side(double dimension_m, float resolution) {
+    return (int)std::round((float)dimension_m / resolution);
+}
+
+void build_expected_points(int n, std::vector<float>& table) {
+    const float vertical_point_ang_dist = 0.00174532925 * 2;  // GroundSegmentation.h:69
+    table.assign((size_t)n * n, 0.0f);
+    const size_t cells = (size_t)n;
+    for (size_t i = 0; i < cells; ++i)
+        for (size_t j = 0; j < cells; ++j) {
+            const float dist = std::hypot(i - cells / 2.0, j - cells / 2.0);
+            table[i + j * cells] = std::atan(1 / dist) / vertical_point_ang_dist;
+        }
+}
+
+// grid_map::GridMap::setGeometry + the constants the kernels need; squares are written as
+// x * x, which is what the reference's compiler emits for std::pow(x, 2.0).
+void derive_constants(const gg_config& c, double dimension_m, float resolution, unsigned flags, Const& k) {
+    const double res = (double)resolution;
+    const int n = (int)std::round((double)(float)dimension_m / res);
+    k.N = n;
+    k.N2 = n * n;
+    k.max_ring = c.max_ring;
+    k.full_layers = (flags & GG_FLAG_FULL_LAYERS) ? 1 : 0;
+    k.pc_var_thresh_f = (float)c.point_count_cell_variance_threshold;
+    k.res_f = (float)res;
+    k.res = res;
+    k.len = (double)n * res;
+    k.half = 0.5 * k.len;
+    k.res_sq = (double)k.res_f * (double)k.res_f;
+    k.min_outlier_conf = c.min_outlier_detection_ground_confidence;
+    k.outlier_tol = c.outlier_tolerance;
+    k.gp_thresh = c.ground_patch_detection_minimum_point_count_threshold;
+    k.df_sq = c.distance_factor * c.distance_factor;
+    k.mdf_sq = c.minimum_distance_factor * c.minimum_distance_factor;
+    const double m10 = c.minimum_distance_factor * 10;
+    k.mdf10_sq = m10 * m10;
+    k.psc_sq = c.patch_size_change_distance * c.patch_size_change_distance;
+    k.occ_factor = c.occupied_cells_point_count_factor;
+    k.occ_factor2 = c.occupied_cells_point_count_factor * 2.0f;
+    k.dec_factor = c.occupied_cells_decrease_factor;
+    k.lab_fac = c.minimum_distance_factor * 5;
+    k.lab_thres = c.miminum_point_height_threshold;
+    k.lab_obs = c.minimum_point_height_obstacle_threshold;
+}
+
+// grid_map::GridMap::move (getIndexShiftFromPositionShift / getPositionShiftFromIndexShift):
+// whole-cell shift, rounded half away from zero; the map position advances by the aligned
+// shift.  Returns the buffer index shift: new(r, c) = old(r + shift_i, c + shift_j).
+void move_map(double res, double& px, double& py, double nx, double ny, int& shift_i, int& shift_j) {
+    const double tx = (nx - px) / res, ty = (ny - py) / res;
+    const int cx = (int)(tx + 0.5 * (tx > 0 ? 1 : -1));
+    const int cy = (int)(ty + 0.5 * (ty > 0 ? 1 : -1));
+    shift_i = -cx;
+    shift_j = -cy;
+    px += (double)cx * res;
+    py += (double)cy * res;
+}
+
+// Wavefront schedule of GroundSegmentation::spiral_ground_interpolation (:398-441).
+// Every visit reads the 3x3 neighbourhood of G and C and writes its own cell (:453-464).
+// level(v) = 1 + max(level of the last writer of any cell it reads, level of any earlier
+// reader of the cell it writes); visits of one level are mutually independent, so running
+// the levels in order reproduces the sequential sweep exactly.
+void build_spiral_schedule(int n, std::vector<int>& level_start, std::vector<uint32_t>& visits) {
+    const int c = n / 2 - 1;
+    std::vector<int> last_write((size_t)n * n, -1), last_read((size_t)n * n, -1);
+    std::vector<uint32_t> seq;
+    std::vector<int> lvl;
+    auto visit = [&](int x, int y) {
+        int l = 0;
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) l = std::max(l, last_write[(x + dx) + (size_t)(y + dy) * n] + 1);
+        l = std::max(l, last_read[x + (size_t)y * n] + 1);
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                int& r = last_read[(x + dx) + (size_t)(y + dy) * n];
+                r = std::max(r, l);
+            }
+        last_write[x + (size_t)y * n] = l;
+        seq.push_back((uint32_t)x | ((uint32_t)y << 16));
+        lvl.push_back(l);
+    };
+    for (int p = c - 1; p >= 1; --p) {
+        const int side = (c - p) * 2;
+        const int q = p + side;
+        for (int pos = p; pos < q; ++pos) visit(p, pos);       // side 0: x fixed
+        for (int pos = p; pos < q; ++pos) visit(pos, p);       // side 1: y fixed
+        for (int pos = q; pos >= p; --pos) visit(q, pos);      // far sides, descending
+        for (int pos = q; pos >= p; --pos) visit(pos, q);
+    }
+    int levels = 0;
+    for (int l : lvl) levels = std::max(levels, l + 1);
+    level_start.assign((size_t)levels + 1, 0);
+    for (int l : lvl) ++level_start[(size_t)l + 1];
+    for (int l = 0; l < levels; ++l) level_start[(size_t)l + 1] += level_start[l];
+    visits.resize(seq.size());
+    std::vector<int> cursor(level_start.begin(), level_start.end() - 1);
+    for (size_t v = 0; v < seq.size(); ++v) visits[(size_t)cursor[lvl[v]]++] = seq[v];
+}
+
+}  // namespace gg
+
+extern "C" {
+
+int gg_host_cells_per_side(double dimension_m, float resolution) { return gg::cells_per_side(dimension_m, resolution); }
+
+int gg_host_expected_points(double dimension_m, float resolution, float* dst) {
+    std::vector<float> t;
+    const int n = gg::cells_per_side(dimension_m, resolution);
+    gg::build_expected_points(n, t);
+    std::memcpy(dst, t.data(), t.size() * sizeof(float));
+    return n;
+}
+
+int gg_host_spiral_schedule(int n, int* level_start, int level_cap, uint32_t* visits, int visit_cap, int* n_levels, int* n_visits) {
+    std::vector<int> ls;
+    std::vector<uint32_t> vs;
+    gg::build_spiral_schedule(n, ls, vs);
+    *n_levels = (int)ls.size() - 1;
+    *n_visits = (int)vs.size();
+    if (level_start && level_cap >= (int)ls.size()) std::memcpy(level_start, ls.data(), ls.size() * sizeof(int));
+    if (visits && visit_cap >= (int)vs.size()) std::memcpy(visits, vs.data(), vs.size() * sizeof(uint32_t));
+    return 0;
+}
+
+int gg_host_move_map(double res, double* pos_xy, double nx, double ny, int* shift_ij) {
+    gg::move_map(res, pos_xy[0], pos_xy[1], nx, ny, shift_ij[0], shift_ij[1]);
+    return (shift_ij[0] != 0 || shift_ij[1] != 0) ? 1 : 0;
+}
+}

@@ -1,0 +1,134 @@
+// Internal definitions shared by the kernels (gg_kernels.cu) and the C-ABI (gg_capi.cu).
+// Not installed; the public boundary is include/groundgrid_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "groundgrid_b200.h"
+
+namespace gg {
+
+// ---- device layer slots (per map slot, each N*N floats, column-major) -------------------
+// "ground" and "groundpatch" come first and are contiguous: they are the rolling terrain
+// prior, the only state that survives a scan and what NCCL broadcasts.
+enum Layer : int {
+    L_GROUND = 0,       // "ground"            terrain height G
+    L_GROUNDPATCH = 1,  // "groundpatch"       confidence C
+    L_OBSTACLES = 2,    // "points" after labelling: non-ground points per cell (GroundSegmentation.cpp:147,176)
+    L_VARIANCE = 3,     // "variance"          m2 / (count + FLT_MIN)            (:323)
+    L_MINH = 4,         // "minGroundHeight"
+    L_COUNT = 5,        // "points" during rasterisation: kept points per cell   (:309)
+    L_MAXH = 6,         // "maxGroundHeight"   (dead layer)
+    L_GCAND = 7,        // "groundCandidates"  (dead layer)
+    L_PLANEDIST = 8,    // "planeDist"         (dead layer)
+    L_M2 = 9,           // "m2"
+    L_MEAN = 10,        // "meanVariance"      Welford mean
+    L_RAW = 11,         // "pointsRaw"         (dead layer)
+    L_NUM = 12,
+    L_NUM_LIVE = 6,     // layers [0, 6) exist always; [6, 12) only with GG_FLAG_FULL_LAYERS
+};
+
+// per-point class codes (upper byte of PointAux code)
+enum PointClass : unsigned {
+    PC_ABSENT = 0,          // outside the map / NaN: never part of the output cloud
+    PC_KEPT = 1,            // rasterised, labelled by the height test
+    PC_KEPT_BORDER = 2,     // rasterised, but cell index >= N-3: vanishes from the output (:167-168)
+    PC_IGNORED = 3,         // ring > max_ring or closer than sqrt(12) m: labelled, not rasterised (:237-240)
+    PC_IGNORED_BORDER = 4,  // ignored and in a border cell: vanishes
+    PC_OUTLIER = 5,         // below-ground outlier: always labelled ground (:270,185-189)
+};
+
+// Constants derived once per set_config on the host, with the reference's own expressions
+// (so the fp64 values are what the reference's compiler computes).
+struct Const {
+    int N, N2;
+    int max_ring;
+    int full_layers;
+    float pc_var_thresh_f;  // (float) point_count_cell_variance_threshold (float >= int compare, :374)
+    float res_f;            // (float) map.getResolution()
+    double res;             // map.getResolution()  == (double) res_f
+    double len, half;       // N * res, 0.5 * len
+    double res_sq;          // res * res  (std::pow(resolution, 2.0), :332,356,463)
+    double min_outlier_conf, outlier_tol;
+    double gp_thresh;       // ground_patch_detection_minimum_point_count_threshold
+    double df_sq, mdf_sq, mdf10_sq, psc_sq;
+    double occ_factor, occ_factor2, dec_factor;
+    double lab_fac, lab_thres, lab_obs;
+};
+
+// Per-scan, per-slot parameters (changes every scan / pose update).
+struct SlotParams {
+    double px, py;        // map centre position
+    double t20, t21, t22, t23;  // row 2 of T_base_from_map (seed of exposed cells)
+    float ox, oy, oz;     // cloud origin
+    float base_z_f;       // (float) base_z
+    int n_points;
+    int shift_i, shift_j; // pending roll (index shift): new(r,c) = old(r + shift_i, c + shift_j)
+    int slot;
+    const gg_point* src;  // device pointer of this scan's cloud (the slot's own buffer or a caller-owned one)
+};
+
+// Pointers / strides of the handle's device arena, passed to kernels by value.
+struct View {
+    Const k;
+    float* layers;        // [n_slots][n_layers][N2]
+    int n_layers;
+    const float* expected;  // [N2] expectedPoints table (GroundSegmentation.cpp:40-46)
+    gg_point* points;     // [n_slots][pcap]
+    uint32_t* key;        // [n_slots][pcap] cell index of kept points, N2 for everything else
+    uint32_t* key2;       // sort ping-pong
+    float* zval;          // [n_slots][pcap] z per input point
+    float* z2;            // sort ping-pong
+    float* zsorted;       // [n_slots][pcap] z of kept points grouped by cell, input order inside a cell
+    float* dist;          // [n_slots][pcap] hypotf(x - ox, y - oy)
+    uint32_t* code;       // [n_slots][pcap] class << 24 | cell
+    uint8_t* labels;      // [n_slots][pcap]
+    int* cnt_i;           // [n_slots][N2] kept points per cell
+    int* raw_i;           // [n_slots][N2] inside points per cell (full layers)
+    int* cellstart;       // [n_slots][N2] exclusive scan of cnt_i
+    int* sort_hist;       // [n_slots][digits * sort_blocks]
+    uint32_t* out_index;  // [n_slots][pcap]
+    int* out_counts;      // [n_slots][3 * out_blocks + 1]  (+1: n_out)
+    gg_point* out_cloud;  // [n_slots][pcap] (allocated lazily)
+    float* roll_scratch;  // [n_slots][2][N2]
+    size_t pcap;
+    int sort_blocks;      // ceil(pcap / SORT_TILE)
+    int out_blocks;       // ceil(pcap / OUT_TILE)
+    int key_bits, bits_lo, bits_hi;
+    // spiral wavefront schedule (shared by all slots)
+    const int* level_start;   // [levels + 1]
+    const uint32_t* visits;   // [n_visits]  x | y << 16
+    int levels;
+
+    __host__ __device__ float* layer(int slot, int l) const { return layers + ((size_t)slot * n_layers + l) * k.N2; }
+};
+
+constexpr int SORT_TILE = 2048;
+constexpr int SORT_THREADS = 256;
+constexpr int OUT_TILE = 1024;
+
+// kernels of the pipeline, as reported by the profiling hooks (gg_profile_read)
+enum KernelId : int {
+    K_CLEAR = 0, K_RASTERIZE, K_SORT_HIST1, K_SORT_SCAN1, K_SORT_SCATTER1, K_SORT_HIST2, K_SORT_SCAN2, K_SORT_SCATTER2,
+    K_SCAN_CELLS, K_CELL_STATS, K_DETECT, K_SPIRAL, K_LABEL, K_ROLL_GATHER, K_ROLL_COMMIT, K_OUT_COUNT, K_OUT_SCAN,
+    K_OUT_WRITE, K_NUM
+};
+
+// Optional per-kernel CUDA-event timing (bench.py's roofline needs the dominant kernel's own
+// duration measured live on the launching stream).  Null = no events.
+struct Profiler {
+    virtual void begin(int kernel_id, cudaStream_t st) = 0;
+    virtual void end(int kernel_id, cudaStream_t st) = 0;
+    virtual ~Profiler() {}
+};
+
+// ---- launchers (gg_kernels.cu); every function enqueues on `st` and returns the number of
+// kernel launches it issued (for gg_kernel_launches()). -----------------------------------
+int launch_init_map(const View& v, int slot, float z, cudaStream_t st);
+int launch_roll(const View& v, const SlotParams* batch, int count, cudaStream_t st, Profiler* prof);
+int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int max_points, int stop_after, cudaStream_t st,
+                         Profiler* prof);
+int launch_output(const View& v, const SlotParams* batch, int count, int max_points, bool want_cloud, cudaStream_t st,
+                  Profiler* prof);
+
+}  // namespace gg

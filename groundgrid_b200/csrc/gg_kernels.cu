@@ -1,0 +1,760 @@
+// groundgrid_b200 -- hand-written sm_100a kernels of the GroundGrid per-scan hot path.
+//
+// Phases (reference: src/GroundSegmentation.cpp, see DESIGN.md for the data layout):
+//   k_rasterize     point -> cell, ignore test, outlier ray-march            (:200-280)
+//   k_sort_*        stable LSD radix sort of kept points by cell (input order kept inside a
+//                   cell, because the Welford recurrence of :298-305 is order dependent)
+//   k_cell_stats    per-cell sequential count / min / Welford mean+M2 -> variance (:282-309,323)
+//   k_detect        3x3 / 5x5 ground-patch stencil updating G, C              (:314-395)
+//   k_spiral        level-scheduled wavefront of the in-place spiral sweep    (:398-465)
+//   k_label         per-point ground / non-ground decision                    (:146-196)
+//   k_out_*         output cloud order: kept, ignored, outliers               (:112-117,150,185)
+//   k_roll_*        GroundGrid::update: whole-cell roll + seeding             (GroundGrid.cpp:83-147)
+//
+// Arithmetic rules: no FMA contraction (compiled with --fmad=false AND
+// written with __f*_rn intrinsics where a product feeds a sum), IEEE division / sqrt,
+// fp64 wherever the reference's C++ promotes to double, Eigen 3.3.7's binary-split
+// reduction order for every fixed-size block sum.
+#include <cfloat>
+#include <cstdio>
+
+#include "gg_internal.h"
+
+namespace gg {
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int trunc_index(double v) {
+    // grid_map: indexVector.cast<int>() (truncation toward zero); clamped so that NaN / huge
+    // values map far outside instead of being undefined.
+    if (!(v == v)) return 1000000000;
+    if (v > 1.0e9) return 1000000000;
+    if (v < -1.0e9) return -1000000000;
+    return __double2int_rz(v);
+}
+
+// grid_map_core getIndexFromPosition with start index (0,0): -(int)((p - len/2 - pos) / res)
+__device__ __forceinline__ void grid_index(const Const& k, double px, double py, double x, double y, int& ix, int& iy) {
+    const double vx = __ddiv_rn(__dsub_rn(__dsub_rn(x, k.half), px), k.res);
+    const double vy = __ddiv_rn(__dsub_rn(__dsub_rn(y, k.half), py), k.res);
+    ix = -trunc_index(vx);
+    iy = -trunc_index(vy);
+}
+
+// grid_map_core checkIfPositionWithinMap: t = -(p - pos - len/2); 0 <= t < len
+__device__ __forceinline__ bool grid_inside(const Const& k, double px, double py, double x, double y) {
+    const double tx = -__dsub_rn(__dsub_rn(x, px), k.half);
+    const double ty = -__dsub_rn(__dsub_rn(y, py), k.half);
+    return tx >= 0.0 && ty >= 0.0 && tx < k.len && ty < k.len;
+}
+
+// Eigen 3.3.7 redux_novec_unroller: binary split over the block's coefficients (column-major).
+template <int Start, int Len>
+struct TreeSum {
+    template <typename F>
+    __device__ __forceinline__ static float run(const F& e) {
+        return __fadd_rn(TreeSum<Start, Len / 2>::run(e), TreeSum<Start + Len / 2, Len - Len / 2>::run(e));
+    }
+};
+template <int Start>
+struct TreeSum<Start, 1> {
+    template <typename F>
+    __device__ __forceinline__ static float run(const F& e) {
+        return e(Start);
+    }
+};
+
+__device__ __forceinline__ float tree9(const float* e) {
+    return __fadd_rn(__fadd_rn(__fadd_rn(e[0], e[1]), __fadd_rn(e[2], e[3])),
+                     __fadd_rn(__fadd_rn(e[4], e[5]), __fadd_rn(e[6], __fadd_rn(e[7], e[8]))));
+}
+
+__device__ __forceinline__ int warp_inclusive_scan(int v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// Exclusive scan of n ints (in -> out, may alias) by one block of 1024 threads.
+// Returns the grand total to every thread.
+__device__ int block_exclusive_scan_1024(const int* in, int* out, int n) {
+    __shared__ int s_warp[32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int per = (n + 1023) / 1024;
+    const int begin = min(tid * per, n), end = min(begin + per, n);
+    int sum = 0;
+    for (int j = begin; j < end; ++j) sum += in[j];
+    const int incl = warp_inclusive_scan(sum);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = s_warp[lane];
+        const int wi = warp_inclusive_scan(w);
+        s_warp[lane] = wi - w;
+        if (lane == 31) s_total = wi;
+    }
+    __syncthreads();
+    int run = incl - sum + s_warp[warp];
+    for (int j = begin; j < end; ++j) {
+        const int t = in[j];
+        out[j] = run;
+        run += t;
+    }
+    const int total = s_total;
+    __syncthreads();
+    return total;
+}
+
+// ------------------------------------------------------------------------------------------
+// fills / map init / roll
+// ------------------------------------------------------------------------------------------
+__global__ void k_fill(float* __restrict__ p, size_t n, float val) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = val;
+}
+
+// GroundGrid::update (GroundGrid.cpp:96-133,143): new(r, c) = old(r + shift_i, c + shift_j);
+// exposed cells: ground = -(T * (cx, cy, 0)).z in fp64, groundpatch = 0.
+__global__ void __launch_bounds__(256) k_roll_gather(View v, const SlotParams* __restrict__ batch) {
+    const SlotParams& sp = batch[blockIdx.y];
+    if (sp.shift_i == 0 && sp.shift_j == 0) return;
+    const Const& k = v.k;
+    const int cell = blockIdx.x * 256 + threadIdx.x;
+    if (cell >= k.N2) return;
+    const int N = k.N;
+    const int r = cell % N, c = cell / N;
+    const int orr = r + sp.shift_i, occ = c + sp.shift_j;
+    const float* G = v.layer(sp.slot, L_GROUND);
+    const float* C = v.layer(sp.slot, L_GROUNDPATCH);
+    float* sg = v.roll_scratch + (size_t)sp.slot * 2 * k.N2;
+    float* sc = sg + k.N2;
+    if (orr >= 0 && orr < N && occ >= 0 && occ < N) {
+        sg[cell] = G[orr + occ * N];
+        sc[cell] = C[orr + occ * N];
+    } else {
+        // grid_map getPositionFromIndex: pos + (len/2 - res/2) + res * (-(double)index)
+        const double off = __dsub_rn(k.half, __dmul_rn(0.5, k.res));
+        const double x = __dadd_rn(__dadd_rn(sp.px, off), __dmul_rn(k.res, (double)(-r)));
+        const double y = __dadd_rn(__dadd_rn(sp.py, off), __dmul_rn(k.res, (double)(-c)));
+        // tf2::Transform * Vector3(x, y, 0): row2.dot(v) + origin.z
+        const double tz = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(sp.t20, x), __dmul_rn(sp.t21, y)), __dmul_rn(sp.t22, 0.0)), sp.t23);
+        sg[cell] = (float)(-tz);
+        sc[cell] = 0.0f;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_roll_commit(View v, const SlotParams* __restrict__ batch) {
+    const SlotParams& sp = batch[blockIdx.y];
+    if (sp.shift_i == 0 && sp.shift_j == 0) return;
+    const int cell = blockIdx.x * 256 + threadIdx.x;
+    if (cell >= v.k.N2) return;
+    const float* sg = v.roll_scratch + (size_t)sp.slot * 2 * v.k.N2;
+    v.layer(sp.slot, L_GROUND)[cell] = sg[cell];
+    v.layer(sp.slot, L_GROUNDPATCH)[cell] = sg[v.k.N2 + cell];
+}
+
+// per-scan reset of the accumulators that are built with atomics (the float layers are fully
+// rewritten by k_cell_stats, which replaces the fills of GroundSegmentation.cpp:61-75)
+__global__ void __launch_bounds__(256) k_clear_scan(View v, const SlotParams* __restrict__ batch) {
+    const SlotParams& sp = batch[blockIdx.y];
+    const int cell = blockIdx.x * 256 + threadIdx.x;
+    if (cell >= v.k.N2) return;
+    const size_t off = (size_t)sp.slot * v.k.N2;
+    v.cnt_i[off + cell] = 0;
+    if (v.k.full_layers) v.raw_i[off + cell] = 0;
+    v.layer(sp.slot, L_OBSTACLES)[cell] = 0.0f;  // map["points"].setConstant(0.0), :147
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 1a: per-point rasterisation front end (insert_cloud up to the accumulate step)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rasterize(View v, const SlotParams* __restrict__ batch) {
+    const SlotParams& sp = batch[blockIdx.y];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= sp.n_points) return;
+    const Const& k = v.k;
+    const int N = k.N;
+    const size_t base = (size_t)sp.slot * v.pcap;
+
+    // coalesced 2 x 16-byte loads of the 32-byte PointXYZIR record
+    const uint4* rec = reinterpret_cast<const uint4*>(sp.src + i);
+    const uint4 a = __ldg(rec);
+    const uint4 b = __ldg(rec + 1);
+    const float x = __uint_as_float(a.x), y = __uint_as_float(a.y), z = __uint_as_float(a.z);
+    const int ring = (int)(b.y & 0xffffu);
+    const float ox = sp.ox, oy = sp.oy, oz = sp.oz;
+
+    const float dxo = __fsub_rn(x, ox), dyo = __fsub_rn(y, oy);
+    // std::pow(dx, 2.0) + std::pow(dy, 2.0) in double (:223); the same sum feeds hypotf (:170)
+    const double sq = __dadd_rn(__dmul_rn((double)dxo, (double)dxo), __dmul_rn((double)dyo, (double)dyo));
+    const float sqdist = (float)sq;
+    v.zval[base + i] = z;
+    v.dist[base + i] = (float)__dsqrt_rn(sq);  // glibc hypotf: (float) sqrt((double)x*x + (double)y*y)
+
+    uint32_t key = (uint32_t)k.N2;  // sentinel: not rasterised
+    uint32_t code = PC_ABSENT << 24;
+
+    const double px = sp.px, py = sp.py;
+    int g0, g1;
+    grid_index(k, px, py, (double)x, (double)y, g0, g1);
+    if (grid_inside(k, px, py, (double)x, (double)y) && g0 >= 0 && g1 >= 0 && g0 < N && g1 < N) {
+        const int cell = g0 + g1 * N;
+        const bool border = (N <= g0 + 3) || (N <= g1 + 3);  // :167
+        if (k.full_layers) atomicAdd(v.raw_i + (size_t)sp.slot * k.N2 + cell, 1);  // pointsRaw, :234
+        if (ring > k.max_ring || sqdist < 12.0f) {  // :237
+            code = ((border ? PC_IGNORED_BORDER : PC_IGNORED) << 24) | (uint32_t)cell;
+        } else {
+            const float* G = v.layer(sp.slot, L_GROUND);
+            const float* C = v.layer(sp.slot, L_GROUNDPATCH);
+            bool outlier = false;
+            const float oldg = G[cell];
+            if ((double)z < __dsub_rn((double)oldg, 0.2)) {  // :244
+                float vx = dxo, vy = dyo, vz = __fsub_rn(z, oz);
+                const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz)));
+                vx = __fdiv_rn(vx, len);
+                vy = __fdiv_rn(vy, len);
+                vz = __fdiv_rn(vz, len);
+                const double len2 = __dmul_rn((double)len, (double)len);
+                if (vz < -0.01f) {
+                    // step cap: the reference loop is unbounded for non-finite lengths
+                    for (int step = 3; step < (1 << 20); ++step) {
+                        const float fs = (float)step;
+                        const float sx = __fmul_rn(fs, vx), sy = __fmul_rn(fs, vy), sz = __fmul_rn(fs, vz);
+                        const double lhs = __dadd_rn(__dadd_rn(__dmul_rn((double)sx, (double)sx), __dmul_rn((double)sy, (double)sy)),
+                                                     __dmul_rn((double)sz, (double)sz));
+                        if (!(lhs < len2)) break;
+                        int ix, iy;
+                        grid_index(k, px, py, (double)__fadd_rn(sx, ox), (double)__fadd_rn(sy, oy), ix, iy);
+                        if (ix <= 0 || iy <= 0 || ix >= N - 1 || iy >= N - 1) continue;
+                        const int r0 = max(ix - 1, 2), c0 = max(iy - 1, 2);  // :268 (clamped, not centred)
+                        float e[9];
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) e[q] = C[(r0 + q % 3) + (c0 + q / 3) * N];
+                        const float bs = tree9(e);
+                        if ((double)bs > k.min_outlier_conf && C[ix + iy * N] > 0.01f &&
+                            (double)G[ix + iy * N] >= __dadd_rn((double)__fadd_rn(sz, oz), k.outlier_tol)) {
+                            outlier = true;
+                            break;
+                        }
+                    }
+                }
+            }
+            if (outlier) {
+                code = (PC_OUTLIER << 24) | (uint32_t)cell;
+            } else {
+                key = (uint32_t)cell;
+                code = ((border ? PC_KEPT_BORDER : PC_KEPT) << 24) | (uint32_t)cell;
+                atomicAdd(v.cnt_i + (size_t)sp.slot * k.N2 + cell, 1);
+            }
+        }
+    }
+    v.key[base + i] = key;
+    v.code[base + i] = code;
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 1b: stable LSD radix sort (cell -> z), two passes
+// ------------------------------------------------------------------------------------------
+// per-block digit histogram; hist layout [slot][digit * nb + block]
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(View v, const SlotParams* __restrict__ batch, const uint32_t* __restrict__ keys,
+                                                            int shift, int bits, int nb) {
+    extern __shared__ int s_hist[];
+    const SlotParams& sp = batch[blockIdx.y];
+    const int D = 1 << bits;
+    for (int d = threadIdx.x; d < D; d += SORT_THREADS) s_hist[d] = 0;
+    __syncthreads();
+    const int n = sp.n_points;
+    const uint32_t* kin = keys + (size_t)sp.slot * v.pcap;
+    const int tile0 = blockIdx.x * SORT_TILE;
+    const uint32_t mask = (uint32_t)D - 1u;
+#pragma unroll
+    for (int r = 0; r < SORT_TILE / SORT_THREADS; ++r) {
+        const int idx = tile0 + r * SORT_THREADS + threadIdx.x;
+        if (idx < n) atomicAdd(&s_hist[(kin[idx] >> shift) & mask], 1);
+    }
+    __syncthreads();
+    int* hist = v.sort_hist + (size_t)sp.slot * ((size_t)v.sort_blocks << max(v.bits_lo, v.bits_hi));
+    for (int d = threadIdx.x; d < D; d += SORT_THREADS) hist[d * nb + blockIdx.x] = s_hist[d];
+}
+
+__global__ void __launch_bounds__(1024) k_sort_scan(View v, const SlotParams* __restrict__ batch, int bits, int nb) {
+    const SlotParams& sp = batch[blockIdx.x];
+    int* hist = v.sort_hist + (size_t)sp.slot * ((size_t)v.sort_blocks << max(v.bits_lo, v.bits_hi));
+    block_exclusive_scan_1024(hist, hist, nb << bits);
+}
+
+// Stable scatter.  A block owns SORT_TILE consecutive items and walks them in rounds of
+// SORT_THREADS (thread order == item order).  Ranks inside a round come from
+// __match_any_sync (lanes of a warp) and a warp-ordered pass over the running per-digit
+// counters in shared memory, so equal digits keep their input order.
+template <bool LAST>
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(View v, const SlotParams* __restrict__ batch, const uint32_t* __restrict__ keys_in,
+                                                               const float* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
+                                                               float* __restrict__ vals_out, int shift, int bits, int nb) {
+    extern __shared__ int s_run[];
+    constexpr int ROUNDS = SORT_TILE / SORT_THREADS;
+    constexpr int WARPS = SORT_THREADS / 32;
+    const SlotParams& sp = batch[blockIdx.y];
+    const int D = 1 << bits;
+    for (int d = threadIdx.x; d < D; d += SORT_THREADS) s_run[d] = 0;
+    __syncthreads();
+    const int n = sp.n_points;
+    const size_t base = (size_t)sp.slot * v.pcap;
+    const uint32_t* kin = keys_in + base;
+    const float* vin = vals_in + base;
+    const int tile0 = blockIdx.x * SORT_TILE;
+    const uint32_t mask = (uint32_t)D - 1u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    uint32_t my_key[ROUNDS];
+    float my_val[ROUNDS];
+    int my_rank[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int idx = tile0 + r * SORT_THREADS + threadIdx.x;
+        const bool valid = idx < n;
+        my_key[r] = valid ? kin[idx] : 0u;
+        my_val[r] = valid ? vin[idx] : 0.0f;
+    }
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int idx = tile0 + r * SORT_THREADS + threadIdx.x;
+        const bool valid = idx < n;
+        const int d = valid ? (int)((my_key[r] >> shift) & mask) : D;  // D: matches only other invalid lanes
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int rank_in_warp = __popc(peers & lt_mask);
+        const int total = __popc(peers);
+        int basecnt = 0;
+        for (int w = 0; w < WARPS; ++w) {
+            if (warp == w) {
+                if (valid) basecnt = s_run[d];
+                __syncwarp();
+                if (valid && rank_in_warp == 0) s_run[d] = basecnt + total;
+            }
+            __syncthreads();
+        }
+        my_rank[r] = basecnt + rank_in_warp;
+    }
+    const int* offs = v.sort_hist + (size_t)sp.slot * ((size_t)v.sort_blocks << max(v.bits_lo, v.bits_hi));
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int idx = tile0 + r * SORT_THREADS + threadIdx.x;
+        if (idx < n) {
+            const int d = (int)((my_key[r] >> shift) & mask);
+            const int pos = offs[d * nb + blockIdx.x] + my_rank[r];
+            if (!LAST) keys_out[base + pos] = my_key[r];
+            vals_out[base + pos] = my_val[r];
+        }
+    }
+}
+
+// exclusive scan of the per-cell kept counts -> start of every cell's run in zsorted
+__global__ void __launch_bounds__(1024) k_scan_cells(View v, const SlotParams* __restrict__ batch) {
+    const SlotParams& sp = batch[blockIdx.x];
+    const size_t off = (size_t)sp.slot * v.k.N2;
+    block_exclusive_scan_1024(v.cnt_i + off, v.cellstart + off, v.k.N2);
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 1c: per-cell sequential statistics (the accumulate step of insert_cloud, :282-309,
+// in input order) + variance (:323).  One thread per cell.
+// ------------------------------------------------------------------------------------------
+template <bool FULL>
+__global__ void __launch_bounds__(128) k_cell_stats(View v, const SlotParams* __restrict__ batch) {
+    const SlotParams& sp = batch[blockIdx.y];
+    const Const& k = v.k;
+    const int cell = blockIdx.x * 128 + threadIdx.x;
+    if (cell >= k.N2) return;
+    const size_t coff = (size_t)sp.slot * k.N2;
+    const int cnt = v.cnt_i[coff + cell];
+    const float* zs = v.zsorted + (size_t)sp.slot * v.pcap + v.cellstart[coff + cell];
+    const float oz = sp.oz;
+
+    float n = 0.0f, mean = 0.0f, m2 = 0.0f;
+    float mn = FLT_MAX;
+    float mx = FLT_MIN, gc = 0.0f, pdm = 0.0f;  // dead layers (FULL only)
+    for (int j = 0; j < cnt; ++j) {
+        const float z = zs[j];
+        const float pd = __fsub_rn(z, oz);  // planeDist, :295
+        if (FULL) gc = (float)__ddiv_rn((double)__fadd_rn(z, __fmul_rn(n, gc)), __dadd_rn((double)n, 1.0));  // :296
+        if (mean == 0.0f) mean = pd;  // :298-299
+        if (!(pd != pd)) {            // :300
+            const float delta = __fsub_rn(pd, mean);
+            mean = __fadd_rn(mean, __fdiv_rn(delta, __fadd_rn(n, 1.0f)));
+            if (FULL) pdm = (float)__ddiv_rn((double)__fadd_rn(pd, __fmul_rn(n, pdm)), __dadd_rn((double)n, 1.0));
+            m2 = __fadd_rn(m2, __fmul_rn(delta, __fsub_rn(pd, mean)));
+        }
+        if (FULL) mx = (mx < z) ? z : mx;                   // std::max(maxHeight, z)
+        const float zl = __fsub_rn(z, 0.0001f);
+        mn = (zl < mn) ? zl : mn;                           // std::min(minHeight, z - 0.0001f)
+        n = __fadd_rn(n, 1.0f);
+    }
+    v.layer(sp.slot, L_COUNT)[cell] = n;
+    v.layer(sp.slot, L_VARIANCE)[cell] = __fdiv_rn(m2, __fadd_rn(n, FLT_MIN));
+    v.layer(sp.slot, L_MINH)[cell] = mn;
+    if (FULL) {
+        v.layer(sp.slot, L_M2)[cell] = m2;
+        v.layer(sp.slot, L_MEAN)[cell] = mean;
+        v.layer(sp.slot, L_GCAND)[cell] = gc;
+        v.layer(sp.slot, L_PLANEDIST)[cell] = pdm;
+        v.layer(sp.slot, L_MAXH)[cell] = mx;
+        v.layer(sp.slot, L_RAW)[cell] = (float)v.raw_i[coff + cell];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 2: ground patch detection stencil (detect_ground_patches / detect_ground_patch<S>)
+// ------------------------------------------------------------------------------------------
+constexpr int DT_X = 32, DT_Y = 8, DT_H = 2;
+constexpr int DT_W = DT_X + 2 * DT_H;   // 36
+constexpr int DT_R = DT_Y + 2 * DT_H;   // 12
+
+template <int S>
+__device__ __forceinline__ void detect_patch(const Const& k, const float (*sP)[DT_W], const float (*sV)[DT_W], const float (*sM)[DT_W],
+                                             int li, int lj, float sqdist, float e, float* Gp, float* Cp) {
+    constexpr int H = S / 2;
+    const int r0 = li - H, c0 = lj - H;  // block origin in the shared tile (row index = i, col = j)
+    const float psum = TreeSum<0, S * S>::run([&](int q) { return sP[c0 + q / S][r0 + q % S]; });
+    const float oc = *Cp, og = *Gp;
+
+    // early skipping of (almost) empty areas, :364
+    const double need = floor(__dmul_rn(__dmul_rn(k.gp_thresh, (double)S), (double)e));
+    if ((double)psum < ((need < 3.0) ? 3.0 : need)) return;
+
+    // variance threshold, :369
+    const double a = __dmul_rn((double)sqdist, k.df_sq);
+    const double m = (a < k.mdf_sq) ? k.mdf_sq : a;
+    const float vt = (float)((k.mdf10_sq < m) ? k.mdf10_sq : m);
+
+    const float variance = sV[lj][li];
+    float localmin = sM[c0][r0];
+#pragma unroll
+    for (int q = 1; q < S * S; ++q) {
+        const float t = sM[c0 + q / S][r0 + q % S];
+        localmin = (t < localmin) ? t : localmin;
+    }
+    const float maxVar = (sP[lj][li] >= k.pc_var_thresh_f)
+                             ? variance
+                             : __fdiv_rn(TreeSum<0, S * S>::run([&](int q) { return __fmul_rn(sP[c0 + q / S][r0 + q % S], sV[c0 + q / S][r0 + q % S]); }), psum);
+    const float groundlevel =
+        __fdiv_rn(TreeSum<0, S * S>::run([&](int q) { return __fmul_rn(sP[c0 + q / S][r0 + q % S], sM[c0 + q / S][r0 + q % S]); }), psum);
+    const float gd = __fmul_rn(__fsub_rn(groundlevel, og), __fmul_rn(2.0f, oc));
+    const float groundDiff = (gd < 1.0f) ? 1.0f : gd;  // std::max(gd, 1.0f)
+
+    // do not update known high confidence estimations upward, :379
+    if ((double)oc > 0.5 && (double)groundlevel >= __dadd_rn((double)og, k.outlier_tol)) return;
+
+    if ((double)vt > __dmul_rn((double)maxVar, (double)maxVar) && maxVar > 0.0f &&
+        (double)psum > __dmul_rn((double)__fmul_rn(__fmul_rn(groundDiff, e), (float)S), k.gp_thresh)) {
+        const double ncd = __ddiv_rn((double)psum, k.occ_factor);
+        const float nc = (float)((1.0 < ncd) ? 1.0 : ncd);  // std::min(ncd, 1.0)
+        const float num = __fadd_rn(__fmul_rn(groundlevel, nc), __fmul_rn(__fmul_rn(oc, og), 2.0f));
+        const float den = __fadd_rn(nc, __fmul_rn(oc, 2.0f));
+        *Gp = __fdiv_rn(num, den);
+        const double cd = __ddiv_rn(__dadd_rn(__ddiv_rn((double)psum, k.occ_factor2), (double)oc), 2.0);
+        *Cp = (float)((1.0 < cd) ? 1.0 : cd);
+    } else if (localmin < og) {
+        *Gp = localmin;
+        const float t = __fadd_rn(oc, 0.1f);
+        *Cp = (0.5f < t) ? 0.5f : t;  // std::min(oc + 0.1f, 0.5f)
+    }
+}
+
+__global__ void __launch_bounds__(DT_X* DT_Y) k_detect(View v, const SlotParams* __restrict__ batch) {
+    __shared__ float sP[DT_R][DT_W], sV[DT_R][DT_W], sM[DT_R][DT_W];
+    const SlotParams& sp = batch[blockIdx.z];
+    const Const& k = v.k;
+    const int N = k.N;
+    const int i0 = blockIdx.x * DT_X, j0 = blockIdx.y * DT_Y;
+    const float* P = v.layer(sp.slot, L_COUNT);
+    const float* V = v.layer(sp.slot, L_VARIANCE);
+    const float* M = v.layer(sp.slot, L_MINH);
+    const int tid = threadIdx.y * DT_X + threadIdx.x;
+    for (int t = tid; t < DT_R * DT_W; t += DT_X * DT_Y) {
+        const int lj = t / DT_W, li = t % DT_W;
+        const int gi = i0 - DT_H + li, gj = j0 - DT_H + lj;
+        const bool in = gi >= 0 && gi < N && gj >= 0 && gj < N;
+        const int g = gi + gj * N;
+        sP[lj][li] = in ? P[g] : 0.0f;
+        sV[lj][li] = in ? V[g] : 0.0f;
+        sM[lj][li] = in ? M[g] : FLT_MAX;
+    }
+    __syncthreads();
+    const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
+    if (i < 2 || j < 2 || i >= N - 2 || j >= N - 2) return;  // union of the four sections, :325-328
+    const double di = __dsub_rn((double)i, (double)N / 2.0), dj = __dsub_rn((double)j, (double)N / 2.0);
+    const float sqdist = (float)__dmul_rn(__dadd_rn(__dmul_rn(di, di), __dmul_rn(dj, dj)), k.res_sq);  // :332,356
+    const float e = v.expected[i + j * N];
+    float* Gp = v.layer(sp.slot, L_GROUND) + i + j * N;
+    float* Cp = v.layer(sp.slot, L_GROUNDPATCH) + i + j * N;
+    const int li = threadIdx.x + DT_H, lj = threadIdx.y + DT_H;
+    if ((double)sqdist <= k.psc_sq)
+        detect_patch<3>(k, sP, sV, sM, li, lj, sqdist, e, Gp, Cp);
+    else
+        detect_patch<5>(k, sP, sV, sM, li, lj, sqdist, e, Gp, Cp);
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 3: spiral interpolation as a level-scheduled wavefront (one CTA per scan).
+// The schedule (host-built from the exact RAW/WAR/WAW dependency DAG of the sequential
+// sweep, GroundSegmentation.cpp:413-440) guarantees that visits of one level touch disjoint
+// data, so executing levels in order reproduces the sequential result bit for bit.
+// ------------------------------------------------------------------------------------------
+constexpr int SPIRAL_THREADS = 512;
+
+__global__ void __launch_bounds__(SPIRAL_THREADS) k_spiral(View v, const SlotParams* __restrict__ batch) {
+    const SlotParams& sp = batch[blockIdx.x];
+    const Const& k = v.k;
+    const int N = k.N;
+    float* G = v.layer(sp.slot, L_GROUND);
+    float* C = v.layer(sp.slot, L_GROUNDPATCH);
+    const int cidx = N / 2 - 1;
+    if (threadIdx.x == 0) {
+        C[cidx + cidx * N] = 1.0f;          // :405
+        G[cidx + cidx * N] = sp.base_z_f;   // :411
+    }
+    __syncthreads();
+    const float fc = (float)cidx;
+    for (int lvl = 0; lvl < v.levels; ++lvl) {
+        const int b = v.level_start[lvl], e = v.level_start[lvl + 1];
+        for (int t = b + threadIdx.x; t < e; t += SPIRAL_THREADS) {
+            const uint32_t vis = v.visits[t];
+            const int x = (int)(vis & 0xffffu), y = (int)(vis >> 16);
+            float cc[9], pr[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const int g = (x - 1 + q % 3) + (y - 1 + q / 3) * N;
+                cc[q] = C[g];
+                pr[q] = __fmul_rn(cc[q], G[g]);
+            }
+            const float h = G[x + y * N];
+            const float occ = cc[4];
+            const float s = __fadd_rn(tree9(cc), FLT_MIN);  // :457
+            const float avg = __fdiv_rn(tree9(pr), s);      // :458
+            G[x + y * N] = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, occ), avg), __fmul_rn(occ, h));  // :460
+            const float fx = __fsub_rn((float)x, fc), fy = __fsub_rn((float)y, fc);
+            const double d2 = __dmul_rn(__dadd_rn(__dmul_rn((double)fx, (double)fx), __dmul_rn((double)fy, (double)fy)), k.res_sq);
+            if (d2 > 12.0) {  // :463
+                const double o = (double)occ;
+                const double dec = __dsub_rn(o, __ddiv_rn(o, k.dec_factor));
+                C[x + y * N] = (float)((dec < 0.001) ? 0.001 : dec);  // std::max(dec, 0.001)
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 4: labelling (:146-196)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_label(View v, const SlotParams* __restrict__ batch) {
+    const SlotParams& sp = batch[blockIdx.y];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= sp.n_points) return;
+    const Const& k = v.k;
+    const size_t base = (size_t)sp.slot * v.pcap;
+    const uint32_t code = v.code[base + i];
+    const uint32_t cls = code >> 24;
+    const int cell = (int)(code & 0xffffffu);
+    uint8_t label = GG_LABEL_ABSENT;
+    if (cls == PC_OUTLIER) {
+        label = GG_LABEL_GROUND;
+    } else if (cls == PC_KEPT || cls == PC_IGNORED) {
+        const double groundheight = (double)v.layer(sp.slot, L_GROUND)[cell];
+        const float variance = v.layer(sp.slot, L_VARIANCE)[cell];
+        const float dist = v.dist[base + i];
+        const float z = v.zval[base + i];
+        // std::max(std::min((f * dist) / variance * thres, thres), obs_thres) with C++ min/max semantics
+        const double a = __dmul_rn(__ddiv_rn(__dmul_rn(k.lab_fac, (double)dist), (double)variance), k.lab_thres);
+        double t = (k.lab_thres < a) ? k.lab_thres : a;
+        t = (t < k.lab_obs) ? k.lab_obs : t;
+        if (__dadd_rn(t, groundheight) < (double)z) {
+            label = GG_LABEL_NONGROUND;
+            atomicAdd(v.layer(sp.slot, L_OBSTACLES) + cell, 1.0f);  // small exact integers: order free
+        } else {
+            label = GG_LABEL_GROUND;
+        }
+    }
+    v.labels[base + i] = label;
+}
+
+// ------------------------------------------------------------------------------------------
+// output cloud order: kept (input order), ignored (input order), outliers (input order)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int out_class(uint32_t code) {
+    const uint32_t cls = code >> 24;
+    return cls == PC_KEPT ? 0 : (cls == PC_IGNORED ? 1 : (cls == PC_OUTLIER ? 2 : -1));
+}
+
+__global__ void __launch_bounds__(OUT_TILE) k_out_count(View v, const SlotParams* __restrict__ batch, int nblk) {
+    const SlotParams& sp = batch[blockIdx.y];
+    const int i = blockIdx.x * OUT_TILE + threadIdx.x;
+    const int c = (i < sp.n_points) ? out_class(v.code[(size_t)sp.slot * v.pcap + i]) : -1;
+    int* counts = v.out_counts + (size_t)sp.slot * (3 * v.out_blocks + 1);
+    const int n0 = __syncthreads_count(c == 0);
+    const int n1 = __syncthreads_count(c == 1);
+    const int n2 = __syncthreads_count(c == 2);
+    if (threadIdx.x == 0) {
+        counts[0 * nblk + blockIdx.x] = n0;
+        counts[1 * nblk + blockIdx.x] = n1;
+        counts[2 * nblk + blockIdx.x] = n2;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_out_scan(View v, const SlotParams* __restrict__ batch, int nblk) {
+    const SlotParams& sp = batch[blockIdx.x];
+    int* counts = v.out_counts + (size_t)sp.slot * (3 * v.out_blocks + 1);
+    const int total = block_exclusive_scan_1024(counts, counts, 3 * nblk);
+    if (threadIdx.x == 0) counts[3 * v.out_blocks] = total;
+}
+
+template <bool CLOUD>
+__global__ void __launch_bounds__(OUT_TILE) k_out_write(View v, const SlotParams* __restrict__ batch, int nblk) {
+    __shared__ int s_w[3][32];
+    const SlotParams& sp = batch[blockIdx.y];
+    const size_t base = (size_t)sp.slot * v.pcap;
+    const int i = blockIdx.x * OUT_TILE + threadIdx.x;
+    const int c = (i < sp.n_points) ? out_class(v.code[base + i]) : -1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    int rank_in_warp = 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, c == q);
+        if (c == q) rank_in_warp = __popc(bal & lt_mask);
+        if (lane == 0) s_w[q][warp] = __popc(bal);
+    }
+    __syncthreads();
+    if (warp < 3) {  // warp q scans the 32 warp totals of class q
+        const int w = s_w[warp][lane];
+        const int wi = warp_inclusive_scan(w);
+        s_w[warp][lane] = wi - w;
+    }
+    __syncthreads();
+    if (c < 0) return;
+    const int* counts = v.out_counts + (size_t)sp.slot * (3 * v.out_blocks + 1);
+    const int pos = counts[c * nblk + blockIdx.x] + s_w[c][warp] + rank_in_warp;
+    v.out_index[base + pos] = (uint32_t)i;
+    if (CLOUD) {
+        const uint4* rec = reinterpret_cast<const uint4*>(sp.src + i);
+        uint4 a = rec[0], b = rec[1];
+        b.x = __float_as_uint((float)v.labels[base + i]);  // intensity = 49 / 99 (:175,180,188)
+        uint4* dst = reinterpret_cast<uint4*>(v.out_cloud + base + pos);
+        dst[0] = a;
+        dst[1] = b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+int launch_init_map(const View& v, int slot, float z, cudaStream_t st) {
+    const size_t n = (size_t)v.k.N2;
+    const int blocks = (int)((n + 255) / 256);
+    k_fill<<<blocks, 256, 0, st>>>(v.layer(slot, L_GROUND), n, z);
+    k_fill<<<blocks, 256, 0, st>>>(v.layer(slot, L_GROUNDPATCH), n, (float)0.0000001);
+    k_fill<<<blocks, 256, 0, st>>>(v.layer(slot, L_OBSTACLES), n, 0.0f);
+    k_fill<<<blocks, 256, 0, st>>>(v.layer(slot, L_COUNT), n, 0.0f);
+    k_fill<<<blocks, 256, 0, st>>>(v.layer(slot, L_VARIANCE), n, 0.0f);
+    k_fill<<<blocks, 256, 0, st>>>(v.layer(slot, L_MINH), n, 100.0f);
+    int launches = 6;
+    if (v.k.full_layers) {
+        k_fill<<<blocks, 256, 0, st>>>(v.layer(slot, L_MAXH), n, -100.0f);
+        for (int l : {L_GCAND, L_PLANEDIST, L_M2, L_MEAN, L_RAW}) k_fill<<<blocks, 256, 0, st>>>(v.layer(slot, l), n, 0.0f);
+        launches += 6;
+    }
+    return launches;
+}
+
+struct Mark {
+    Profiler* p;
+    int id;
+    cudaStream_t st;
+    Mark(Profiler* p_, int id_, cudaStream_t st_) : p(p_), id(id_), st(st_) {
+        if (p) p->begin(id, st);
+    }
+    ~Mark() {
+        if (p) p->end(id, st);
+    }
+};
+#define GG_LAUNCH(id, ...)        \
+    do {                          \
+        Mark mark__(prof, id, st);\
+        __VA_ARGS__;              \
+    } while (0)
+
+int launch_roll(const View& v, const SlotParams* batch, int count, cudaStream_t st, Profiler* prof) {
+    dim3 grid(cdiv(v.k.N2, 256), count);
+    GG_LAUNCH(K_ROLL_GATHER, k_roll_gather<<<grid, 256, 0, st>>>(v, batch));
+    GG_LAUNCH(K_ROLL_COMMIT, k_roll_commit<<<grid, 256, 0, st>>>(v, batch));
+    return 2;
+}
+
+int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int max_points, int stop_after, cudaStream_t st,
+                         Profiler* prof) {
+    int launches = 0;
+    const int N2 = v.k.N2;
+    const int pblocks = max(1, cdiv(max_points, 256));
+    const int nb = max(1, cdiv(max_points, SORT_TILE));
+
+    GG_LAUNCH(K_CLEAR, k_clear_scan<<<dim3(cdiv(N2, 256), count), 256, 0, st>>>(v, batch));
+    GG_LAUNCH(K_RASTERIZE, k_rasterize<<<dim3(pblocks, count), 256, 0, st>>>(v, batch));
+    launches += 2;
+
+    // pass 1: low digit, (key, zval) -> (key2, z2)
+    size_t sh = sizeof(int) << v.bits_lo;
+    GG_LAUNCH(K_SORT_HIST1, k_sort_hist<<<dim3(nb, count), SORT_THREADS, sh, st>>>(v, batch, v.key, 0, v.bits_lo, nb));
+    GG_LAUNCH(K_SORT_SCAN1, k_sort_scan<<<count, 1024, 0, st>>>(v, batch, v.bits_lo, nb));
+    GG_LAUNCH(K_SORT_SCATTER1,
+              k_sort_scatter<false><<<dim3(nb, count), SORT_THREADS, sh, st>>>(v, batch, v.key, v.zval, v.key2, v.z2, 0, v.bits_lo, nb));
+    // pass 2: high digit, (key2, z2) -> zsorted
+    sh = sizeof(int) << v.bits_hi;
+    GG_LAUNCH(K_SORT_HIST2, k_sort_hist<<<dim3(nb, count), SORT_THREADS, sh, st>>>(v, batch, v.key2, v.bits_lo, v.bits_hi, nb));
+    GG_LAUNCH(K_SORT_SCAN2, k_sort_scan<<<count, 1024, 0, st>>>(v, batch, v.bits_hi, nb));
+    GG_LAUNCH(K_SORT_SCATTER2, k_sort_scatter<true><<<dim3(nb, count), SORT_THREADS, sh, st>>>(v, batch, v.key2, v.z2, nullptr, v.zsorted,
+                                                                                             v.bits_lo, v.bits_hi, nb));
+    GG_LAUNCH(K_SCAN_CELLS, k_scan_cells<<<count, 1024, 0, st>>>(v, batch));
+    launches += 7;
+
+    if (v.k.full_layers)
+        GG_LAUNCH(K_CELL_STATS, k_cell_stats<true><<<dim3(cdiv(N2, 128), count), 128, 0, st>>>(v, batch));
+    else
+        GG_LAUNCH(K_CELL_STATS, k_cell_stats<false><<<dim3(cdiv(N2, 128), count), 128, 0, st>>>(v, batch));
+    ++launches;
+    if (stop_after == 1) return launches;
+
+    GG_LAUNCH(K_DETECT, k_detect<<<dim3(cdiv(v.k.N, DT_X), cdiv(v.k.N, DT_Y), count), dim3(DT_X, DT_Y), 0, st>>>(v, batch));
+    ++launches;
+    if (stop_after == 2) return launches;
+
+    GG_LAUNCH(K_SPIRAL, k_spiral<<<count, SPIRAL_THREADS, 0, st>>>(v, batch));
+    ++launches;
+    if (stop_after == 3) return launches;
+
+    GG_LAUNCH(K_LABEL, k_label<<<dim3(pblocks, count), 256, 0, st>>>(v, batch));
+    ++launches;
+    return launches;
+}
+
+int launch_output(const View& v, const SlotParams* batch, int count, int max_points, bool want_cloud, cudaStream_t st,
+                  Profiler* prof) {
+    const int nblk = max(1, cdiv(max_points, OUT_TILE));
+    GG_LAUNCH(K_OUT_COUNT, k_out_count<<<dim3(nblk, count), OUT_TILE, 0, st>>>(v, batch, nblk));
+    GG_LAUNCH(K_OUT_SCAN, k_out_scan<<<count, 1024, 0, st>>>(v, batch, nblk));
+    if (want_cloud)
+        GG_LAUNCH(K_OUT_WRITE, k_out_write<true><<<dim3(nblk, count), OUT_TILE, 0, st>>>(v, batch, nblk));
+    else
+        GG_LAUNCH(K_OUT_WRITE, k_out_write<false><<<dim3(nblk, count), OUT_TILE, 0, st>>>(v, batch, nblk));
+    return 3;
+}
+
+}  // namespace gg

@@ -1,0 +1,149 @@
+"""CPU-side checks of the product library: it loads, exports every symbol the header declares,
+refuses to compute without a GPU, and its host-side logic (expectedPoints table, map-move
+arithmetic, spiral wavefront schedule) agrees with the oracle."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from groundgrid_b200 import capi
+from oracle import Oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+f32 = np.float32
+FLT_MIN = f32(np.finfo(np.float32).tiny)
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "groundgrid_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gg_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = capi.load()
+    names = header_symbols()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/groundgrid_b200.h but not exported"
+
+
+def test_struct_layouts_match_the_header():
+    import ctypes as C
+
+    assert C.sizeof(capi.Config) == 8 + 11 * 8 + 8        # 2 ints, 11 doubles, int + padding
+    assert C.sizeof(capi.ScanDesc) == 40
+    assert capi.POINT_DTYPE.itemsize == 32
+    cfg = capi.Config()
+    capi.load().gg_default_config(C.byref(cfg))
+    assert (cfg.point_count_cell_variance_threshold, cfg.max_ring, cfg.thread_count) == (10, 1024, 8)
+    assert (cfg.distance_factor, cfg.minimum_distance_factor, cfg.patch_size_change_distance) == (0.0001, 0.0005, 20.0)
+    assert (cfg.occupied_cells_decrease_factor, cfg.occupied_cells_point_count_factor) == (5.0, 20.0)
+    assert cfg.min_outlier_detection_ground_confidence == 1.25 and cfg.outlier_tolerance == 0.1
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the loud-failure path is for machines without one")
+    with pytest.raises(capi.GroundGridError) as e:
+        capi.GroundGridB200(99.0, 0.33)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+@pytest.mark.parametrize("dim,res,n", [(120.0, 0.33, 364), (99.0, 0.33, 300), (120.0, 0.2, 600), (33.0, 0.33, 100)])
+def test_expected_points_table_matches_oracle(dim, res, n):
+    assert capi.host_cells_per_side(dim, res) == n
+    E = capi.host_expected_points(dim, res)
+    assert np.array_equal(E, Oracle(dim, res).expected_points())
+
+
+def test_move_map_matches_oracle():
+    rng = np.random.default_rng(9)
+    res = float(np.float32(0.33))
+    o = Oracle(33.0, 0.33)
+    o.init_map(1.5, -2.5, 0.0)
+    pos = o.position().copy()
+    T = np.eye(4)[:3]
+    for _ in range(200):
+        target = pos + rng.uniform(-3, 3, 2) * res * rng.choice([0.1, 1.0, 5.0])
+        moved, new_pos, shift = capi.host_move_map(res, pos, target)
+        A = (np.arange(o.n)[:, None] * o.n + np.arange(o.n)[None, :]).astype(np.float32)
+        o.set_layer("ground", A)
+        assert o.update(target[0], target[1], T) == int(moved)
+        assert np.array_equal(o.position(), new_pos)
+        if moved:
+            # oracle content shift must equal the reported index shift: new(r,c) = old(r+si, c+sj)
+            Gn = o.layer("ground")
+            r = np.arange(o.n)[:, None] + shift[0]
+            c = np.arange(o.n)[None, :] + shift[1]
+            ok = (r >= 0) & (r < o.n) & (c >= 0) & (c < o.n)
+            want = (r * o.n + c).astype(np.float32)
+            assert np.array_equal(Gn[ok], want[ok])
+            assert np.all(o.layer("groundpatch")[~ok] == 0.0)
+        pos = new_pos
+
+
+def _tree9(v):
+    return ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + (v[7] + v[8])))
+
+
+def run_level_schedule(G, C, base_z, level_start, visits, res_f, dec_factor=5.0):
+    """Executes the spiral as the GPU does: level by level, all visits of a level read first, then write."""
+    n = G.shape[0]
+    c = n // 2 - 1
+    G = G.copy()
+    C = C.copy()
+    C[c, c] = 1.0
+    G[c, c] = f32(base_z)
+    res2 = np.float64(f32(res_f)) ** 2
+    for lvl in range(len(level_start) - 1):
+        vs = visits[level_start[lvl]:level_start[lvl + 1]]
+        x, y = vs[:, 0], vs[:, 1]
+        cc = [C[x - 1 + k % 3, y - 1 + k // 3] for k in range(9)]
+        gg = [G[x - 1 + k % 3, y - 1 + k // 3] for k in range(9)]
+        s = _tree9(cc) + FLT_MIN
+        avg = _tree9([a * b for a, b in zip(cc, gg)]) / s
+        occ = cc[4]
+        G[x, y] = (f32(1.0) - occ) * avg + occ * gg[4]
+        fx = (x.astype(np.float32) - f32(c)).astype(np.float64)
+        fy = (y.astype(np.float32) - f32(c)).astype(np.float64)
+        far = (fx * fx + fy * fy) * res2 > 12.0
+        o64 = occ.astype(np.float64)
+        dec = np.maximum(o64 - o64 / np.float64(dec_factor), 0.001).astype(np.float32)
+        C[x[far], y[far]] = dec[far]
+    return G, C
+
+
+@pytest.mark.parametrize("dim,res,levels", [(33.0, 0.33, None), (99.0, 0.33, 743), (120.0, 0.33, 903)])
+def test_spiral_wavefront_schedule_is_exact(dim, res, levels):
+    o = Oracle(dim, res)
+    n = o.n
+    ls, vs = capi.host_spiral_schedule(n)
+    c = n // 2 - 1
+    assert len(vs) == sum(4 * 2 * (c - p) + 2 for p in range(1, c))       # SURVEY App. C visit count
+    if levels is not None:
+        assert len(ls) - 1 == levels                                       # SURVEY App. C DAG depth
+    # no two visits of a level may touch each other's 3x3 neighbourhood writes
+    for lvl in range(0, len(ls) - 1, max(1, (len(ls) - 1) // 40)):
+        v = vs[ls[lvl]:ls[lvl + 1]]
+        cells = v[:, 0] * n + v[:, 1]
+        assert len(np.unique(cells)) == len(cells)
+        written = set(cells.tolist())
+        for (x, y) in v:
+            for dx in (-1, 0, 1):
+                for dy in (-1, 0, 1):
+                    if dx or dy:
+                        assert (x + dx) * n + (y + dy) not in written
+    rng = np.random.default_rng(21)
+    o.init_map(0.0, 0.0, 0.0)
+    G = rng.uniform(-1, 1, (n, n)).astype(np.float32)
+    C = (rng.uniform(0, 1, (n, n)) ** 4).astype(np.float32)
+    o.set_layer("ground", G)
+    o.set_layer("groundpatch", C)
+    o.spiral(0.3)
+    Gs, Cs = run_level_schedule(G, C, 0.3, ls, vs, res)
+    assert np.array_equal(o.layer("ground"), Gs)
+    assert np.array_equal(o.layer("groundpatch"), Cs)
