@@ -231,8 +231,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=64, help="independent streams (maps) per GPU")
-    ap.add_argument("--pool", type=int, default=4, help="distinct ego poses / clouds per stream")
+    ap.add_argument("--streams", type=int, default=256, help="independent streams (maps) per GPU")
+    ap.add_argument("--pool", type=int, default=2, help="distinct ego poses / clouds per stream")
     ap.add_argument("--cpu-scans", type=int, default=300, help="scans of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -344,8 +344,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pts_dev = 0
     e0.record(ext)
+    g.fork_streams()          # every stream of the handle starts after e0 ...
     for _ in range(args.steps):
         pts_dev += int(pts_per_pose[step_device()])
+    g.join_streams()          # ... and e1 is recorded after all of them have drained
     e1.record(ext)
     barrier()
     clocks = clk.stop()
@@ -430,7 +432,7 @@ def main():
                        "streams_per_gpu": B, "poses_per_stream": S, "points_per_scan_mean": P_mean, "cells": N_CELLS,
                        "parallelism": f"scans sharded one-stream-set-per-GPU x{world}, no data-path collective",
                        "l2": f"inputs larger than L2: {B * P_mean * 32 / 1e6:.0f} MB of clouds + {B * 6 * N2 * 4 / 1e6:.0f} MB of layers per step vs 126 MB L2",
-                       "layers": "live layers only (dead layers of SURVEY f2 off)"},
+                       "layers": "live layers only (dead layers of SURVEY f2 off)", "cuda_streams": g.n_streams},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_path": roofline_path,
             "cpu_baseline": cpu, "scans_per_s": value * 1e6 / P_mean,
         }

@@ -102,6 +102,9 @@ def load(build_if_missing=True):
         "gg_set_layer": (i, [vp, i, C.c_char_p, vp]),
         "gg_layer_device_ptr": (i, [vp, i, C.c_char_p, C.POINTER(vp)]),
         "gg_stream": (vp, [vp]),
+        "gg_num_streams": (i, [vp]),
+        "gg_fork_streams": (i, [vp]),
+        "gg_join_streams": (i, [vp]),
         "gg_kernel_launches": (C.c_uint64, [vp]),
         "gg_spiral_schedule_info": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
         # host-only helpers (no device needed)
@@ -237,6 +240,16 @@ class GroundGridB200:
     @property
     def stream(self):
         return self._l.gg_stream(self._h)
+
+    @property
+    def n_streams(self):
+        return self._l.gg_num_streams(self._h)
+
+    def fork_streams(self):
+        _check(self._l.gg_fork_streams(self._h))
+
+    def join_streams(self):
+        _check(self._l.gg_join_streams(self._h))
 
     @property
     def kernel_launches(self):

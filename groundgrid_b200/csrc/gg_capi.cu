@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -33,8 +34,8 @@ int fail(int code, const char* fmt, ...) {
         if (e__ != cudaSuccess) return fail(GG_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
-constexpr int kStreams = 4;
-constexpr int kRing = 16;
+constexpr int kStreams = 8;   // upper bound; GG_STREAMS (default 4) picks how many are used
+constexpr int kRing = 64;
 
 // CUDA-event pairs around every kernel launch while profiling is enabled.
 struct EventProfiler : gg::Profiler {
@@ -196,10 +197,22 @@ int ring_commit(gg_handle h, int pos, int count, cudaStream_t st) {
     gg::SlotParams* host = h->h_ring + (size_t)pos * h->n_slots;
     gg::SlotParams* dev = h->d_ring + (size_t)pos * h->n_slots;
     GG_CUDA(cudaMemcpyAsync(dev, host, (size_t)count * sizeof(gg::SlotParams), cudaMemcpyHostToDevice, st));
+    return GG_OK;
+}
+
+// The entry may be reused once the kernels that read it have finished (they may run on any of
+// the handle's streams, so the event is recorded AFTER the launches, not after the copy).
+int ring_release(gg_handle h, int pos, cudaStream_t st) {
     GG_CUDA(cudaEventRecord(h->ring_ev[pos], st));
     h->ring_used[pos] = true;
     return GG_OK;
 }
+
+// Slots are bound to streams in contiguous groups; everything that touches a slot is enqueued
+// on its stream, so scans of different groups overlap (the latency-bound spiral of one group
+// runs under the bandwidth-bound kernels of another) without any cross-stream dependency.
+int stream_index(gg_handle h, int slot) { return (int)((long long)slot * h->n_streams / h->n_slots); }
+cudaStream_t stream_of(gg_handle h, int slot) { return h->streams[stream_index(h, slot)]; }
 
 void fill_params(gg_handle h, const gg_scan_desc& d, gg::SlotParams& p, const gg_point* src) {
     const SlotState& s = h->slots[d.slot];
@@ -215,33 +228,41 @@ void fill_params(gg_handle h, const gg_scan_desc& d, gg::SlotParams& p, const gg
     p.src = src ? src : h->view.points + (size_t)d.slot * h->pcap;
 }
 
-// enqueue the kernels of `count` scans on stream `st`
-int run_scans_on(gg_handle h, int count, const gg_scan_desc* scans, int stop_after, cudaStream_t st,
-                 const gg_point* const* dev_points = nullptr) {
+// enqueue the kernels of `count` scans, each group of slots on its own stream
+int run_scans_grouped(gg_handle h, int count, const gg_scan_desc* scans, int stop_after, const gg_point* const* dev_points = nullptr) {
     if (count <= 0) return GG_OK;
     if (count > h->n_slots) return fail(GG_E_ARG, "count %d exceeds the number of slots %d", count, h->n_slots);
-    gg::SlotParams *hp = nullptr, *dp = nullptr;
-    int pos = 0;
-    int rc = ring_acquire(h, &hp, &dp, &pos);
-    if (rc) return rc;
-    int max_points = 0;
+    int rc;
     for (int i = 0; i < count; ++i) {
         const gg_scan_desc& d = scans[i];
         if ((rc = check_slot(h, d.slot))) return rc;
         if (!h->slots[d.slot].have_map) return fail(GG_E_STATE, "slot %d: map not initialised", d.slot);
         if (d.n_points > h->pcap) return fail(GG_E_ARG, "slot %d: %zu points exceed capacity %zu", d.slot, d.n_points, h->pcap);
-        fill_params(h, d, hp[i], dev_points ? dev_points[i] : nullptr);
-        max_points = std::max(max_points, (int)d.n_points);
-        SlotState& s = h->slots[d.slot];
-        s.n_points = d.n_points;
-        s.last_stop = stop_after;
-        s.ran = true;
-        s.output_valid = false;
-        s.src = dev_points ? dev_points[i] : nullptr;
     }
-    if ((rc = ring_commit(h, pos, count, st))) return rc;
-    h->launches += gg::launch_scan_pipeline(h->view, dp, count, max_points, stop_after, st, h->prof);
-    GG_CUDA(cudaGetLastError());
+    for (int g = 0; g < h->n_streams; ++g) {
+        gg::SlotParams *hp = nullptr, *dp = nullptr;
+        int pos = 0, m = 0, max_points = 0;
+        for (int i = 0; i < count; ++i) {
+            const gg_scan_desc& d = scans[i];
+            if (stream_index(h, d.slot) != g) continue;
+            if (m == 0 && (rc = ring_acquire(h, &hp, &dp, &pos))) return rc;
+            fill_params(h, d, hp[m], dev_points ? dev_points[i] : nullptr);
+            ++m;
+            max_points = std::max(max_points, (int)d.n_points);
+            SlotState& s = h->slots[d.slot];
+            s.n_points = d.n_points;
+            s.last_stop = stop_after;
+            s.ran = true;
+            s.output_valid = false;
+            s.src = dev_points ? dev_points[i] : nullptr;
+        }
+        if (m == 0) continue;
+        cudaStream_t st = h->streams[g];
+        if ((rc = ring_commit(h, pos, m, st))) return rc;
+        h->launches += gg::launch_scan_pipeline(h->view, dp, m, max_points, stop_after, st, h->prof);
+        GG_CUDA(cudaGetLastError());
+        if ((rc = ring_release(h, pos, st))) return rc;
+    }
     return GG_OK;
 }
 
@@ -268,6 +289,7 @@ int run_output_on(gg_handle h, int slot, bool want_cloud, cudaStream_t st) {
     if ((rc = ring_commit(h, pos, 1, st))) return rc;
     h->launches += gg::launch_output(h->view, dp, 1, (int)s.n_points, want_cloud, st, h->prof);
     GG_CUDA(cudaGetLastError());
+    if ((rc = ring_release(h, pos, st))) return rc;
     s.output_valid = true;
     return GG_OK;
 }
@@ -325,8 +347,9 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
     gg::View& v = h->view;
     gg::derive_constants(h->cfg, dimension_m, resolution, flags, v.k);
     if (v.k.N != n) {
+        const int n_geo = v.k.N;
         delete h;
-        return fail(GG_E_ARG, "cell count mismatch between init (%d) and setGeometry (%d)", n, v.k.N);
+        return fail(GG_E_ARG, "cell count mismatch between init (%d) and setGeometry (%d)", n, n_geo);
     }
     const size_t N2 = (size_t)v.k.N2;
     v.n_layers = (flags & GG_FLAG_FULL_LAYERS) ? gg::L_NUM : gg::L_NUM_LIVE;
@@ -401,6 +424,21 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
         h->sched_levels = v.levels;
         h->sched_visits = (int)vs.size();
         for (size_t l = 0; l + 1 < ls.size(); ++l) h->sched_max = std::max(h->sched_max, ls[l + 1] - ls[l]);
+        // records of the pipelined spiral kernel (GG_SPIRAL_DIST=0 selects the plain wavefront kernel)
+        v.spiral_recs = nullptr;
+        v.spiral_dist = 0;
+        v.spiral_threads = h->sched_max <= 512 ? 512 : 1024;
+        int dist = 2;
+        if (const char* e = getenv("GG_SPIRAL_DIST")) dist = atoi(e);
+        std::vector<uint32_t> rc;
+        int max_recent = 0;
+        if (dist >= 1 && dist <= 3 && h->sched_max <= 1024 && gg::build_spiral_records(n, v.k.res_sq, ls, vs, dist, rc, max_recent)) {
+            uint32_t* d_rc = nullptr;
+            GG_TRY(dev_alloc(h, &d_rc, rc.size() + 4));
+            GG_CUDA_TRY(cudaMemcpy(d_rc, rc.data(), rc.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            v.spiral_recs = reinterpret_cast<const uint4*>(d_rc);
+            v.spiral_dist = dist;
+        }
     }
 
     if (stream) {
@@ -408,7 +446,10 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
         h->n_streams = 1;
         h->streams[0] = static_cast<cudaStream_t>(stream);
     } else {
-        for (int i = 0; i < kStreams; ++i) GG_CUDA_TRY(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+        int want = 4;
+        if (const char* e = getenv("GG_STREAMS")) want = atoi(e);
+        h->n_streams = std::max(1, std::min(std::min(want, kStreams), n_slots));
+        for (int i = 0; i < h->n_streams; ++i) GG_CUDA_TRY(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
     }
     GG_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h->h_ring), sizeof(gg::SlotParams) * kRing * S, cudaHostAllocDefault));
     GG_TRY(dev_alloc(h, &h->d_ring, (size_t)kRing * S));
@@ -429,7 +470,7 @@ int gg_destroy(gg_handle h) {
     for (int i = 0; i < kRing; ++i)
         if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
     if (h->own_streams)
-        for (int i = 0; i < kStreams; ++i)
+        for (int i = 0; i < h->n_streams; ++i)
             if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
     delete h;
     return GG_OK;
@@ -470,7 +511,7 @@ int gg_init_map(gg_handle h, int slot, double x, double y, double z) {
     s.px = x;
     s.py = y;
     s.have_map = true;
-    h->launches += gg::launch_init_map(h->view, slot, (float)z, h->streams[0]);
+    h->launches += gg::launch_init_map(h->view, slot, (float)z, stream_of(h, slot));
     GG_CUDA(cudaGetLastError());
     return GG_OK;
 }
@@ -480,33 +521,42 @@ int gg_update_pose_batch(gg_handle h, int count, const int* slots, const double*
     if (count <= 0) return GG_OK;
     if (count > h->n_slots) return fail(GG_E_ARG, "count exceeds slots");
     GG_CUDA(cudaSetDevice(h->device));
-    gg::SlotParams *hp = nullptr, *dp = nullptr;
-    int pos = 0, rc;
-    if ((rc = ring_acquire(h, &hp, &dp, &pos))) return rc;
-    int any = 0;
+    int rc;
     for (int i = 0; i < count; ++i) {
         if ((rc = check_slot(h, slots[i]))) return rc;
-        SlotState& s = h->slots[slots[i]];
-        if (!s.have_map) return fail(GG_E_STATE, "slot %d: map not initialised", slots[i]);
-        gg::SlotParams& p = hp[i];
-        std::memset(&p, 0, sizeof(p));
-        gg::move_map(h->view.k.res, s.px, s.py, xy[2 * i], xy[2 * i + 1], p.shift_i, p.shift_j);
-        p.px = s.px;
-        p.py = s.py;
-        const double* t = T + 12 * (size_t)i;
-        p.t20 = t[8];
-        p.t21 = t[9];
-        p.t22 = t[10];
-        p.t23 = t[11];
-        p.slot = slots[i];
-        const int m = (p.shift_i != 0 || p.shift_j != 0) ? 1 : 0;
-        if (moved) moved[i] = m;
-        any |= m;
+        if (!h->slots[slots[i]].have_map) return fail(GG_E_STATE, "slot %d: map not initialised", slots[i]);
     }
-    if (!any) return GG_OK;  // "We havent moved so we have nothing to do", GroundGrid.cpp:136-137
-    if ((rc = ring_commit(h, pos, count, h->streams[0]))) return rc;
-    h->launches += gg::launch_roll(h->view, dp, count, h->streams[0], h->prof);
-    GG_CUDA(cudaGetLastError());
+    for (int g = 0; g < h->n_streams; ++g) {
+        gg::SlotParams *hp = nullptr, *dp = nullptr;
+        int pos = 0, m = 0, any = 0;
+        for (int i = 0; i < count; ++i) {
+            if (stream_index(h, slots[i]) != g) continue;
+            if (m == 0 && (rc = ring_acquire(h, &hp, &dp, &pos))) return rc;
+            SlotState& s = h->slots[slots[i]];
+            gg::SlotParams& p = hp[m++];
+            std::memset(&p, 0, sizeof(p));
+            gg::move_map(h->view.k.res, s.px, s.py, xy[2 * i], xy[2 * i + 1], p.shift_i, p.shift_j);
+            p.px = s.px;
+            p.py = s.py;
+            const double* t = T + 12 * (size_t)i;
+            p.t20 = t[8];
+            p.t21 = t[9];
+            p.t22 = t[10];
+            p.t23 = t[11];
+            p.slot = slots[i];
+            const int mv = (p.shift_i != 0 || p.shift_j != 0) ? 1 : 0;
+            if (moved) moved[i] = mv;
+            any |= mv;
+        }
+        if (m == 0) continue;
+        cudaStream_t st = h->streams[g];
+        if (any) {  // else: "We havent moved so we have nothing to do", GroundGrid.cpp:136-137
+            if ((rc = ring_commit(h, pos, m, st))) return rc;
+            h->launches += gg::launch_roll(h->view, dp, m, st, h->prof);
+            GG_CUDA(cudaGetLastError());
+        }
+        if ((rc = ring_release(h, pos, st))) return rc;
+    }
     return GG_OK;
 }
 
@@ -538,7 +588,7 @@ int gg_upload_points(gg_handle h, int slot, const gg_point* points, size_t n) {
     if (n > h->pcap) return fail(GG_E_ARG, "%zu points exceed capacity %zu", n, h->pcap);
     if (n && !points) return fail(GG_E_ARG, "null points");
     GG_CUDA(cudaSetDevice(h->device));
-    if (n) GG_CUDA(cudaMemcpyAsync(h->view.points + (size_t)slot * h->pcap, points, n * sizeof(gg_point), cudaMemcpyHostToDevice, h->streams[0]));
+    if (n) GG_CUDA(cudaMemcpyAsync(h->view.points + (size_t)slot * h->pcap, points, n * sizeof(gg_point), cudaMemcpyHostToDevice, stream_of(h, slot)));
     h->slots[slot].n_points = n;
     return GG_OK;
 }
@@ -547,7 +597,7 @@ int gg_run_scans(gg_handle h, int count, const gg_scan_desc* scans, int stop_aft
     if (!h || !scans) return fail(GG_E_ARG, "null argument");
     if (stop_after < 0 || stop_after > 3) return fail(GG_E_ARG, "stop_after must be 0..3");
     GG_CUDA(cudaSetDevice(h->device));
-    return run_scans_on(h, count, scans, stop_after, h->streams[0]);
+    return run_scans_grouped(h, count, scans, stop_after);
 }
 
 int gg_run_scans_device(gg_handle h, int count, const gg_scan_desc* scans, const gg_point* const* dev_points, int stop_after) {
@@ -556,7 +606,7 @@ int gg_run_scans_device(gg_handle h, int count, const gg_scan_desc* scans, const
     for (int i = 0; i < count; ++i)
         if (!dev_points[i] && scans[i].n_points) return fail(GG_E_ARG, "scan %d: null device cloud", i);
     GG_CUDA(cudaSetDevice(h->device));
-    return run_scans_on(h, count, scans, stop_after, h->streams[0], dev_points);
+    return run_scans_grouped(h, count, scans, stop_after, dev_points);
 }
 
 int gg_profile_enable(gg_handle h, int on) {
@@ -604,7 +654,7 @@ int gg_download_labels(gg_handle h, int slot, uint8_t* labels_out, size_t n) {
     if (rc) return rc;
     if (n > h->pcap || (n && !labels_out)) return fail(GG_E_ARG, "bad label buffer");
     GG_CUDA(cudaSetDevice(h->device));
-    if (n) GG_CUDA(cudaMemcpyAsync(labels_out, h->view.labels + (size_t)slot * h->pcap, n, cudaMemcpyDeviceToHost, h->streams[0]));
+    if (n) GG_CUDA(cudaMemcpyAsync(labels_out, h->view.labels + (size_t)slot * h->pcap, n, cudaMemcpyDeviceToHost, stream_of(h, slot)));
     return GG_OK;
 }
 
@@ -619,7 +669,7 @@ int gg_get_output(gg_handle h, int slot, uint32_t* index_out, gg_point* cloud_ou
     int rc = check_slot(h, slot);
     if (rc) return rc;
     GG_CUDA(cudaSetDevice(h->device));
-    cudaStream_t st = h->streams[0];
+    cudaStream_t st = stream_of(h, slot);
     if ((rc = run_output_on(h, slot, cloud_out != nullptr, st))) return rc;
     int total = 0;
     const gg::View& v = h->view;
@@ -647,10 +697,10 @@ int gg_filter_cloud(gg_handle h, int slot, const gg_point* points, size_t n, con
     d.origin[1] = origin[1];
     d.origin[2] = origin[2];
     d.base_z = base_z;
-    if ((rc = run_scans_on(h, 1, &d, 0, h->streams[0]))) return rc;
+    if ((rc = run_scans_grouped(h, 1, &d, 0))) return rc;
     if (labels_out && (rc = gg_download_labels(h, slot, labels_out, n))) return rc;
     if (index_out || cloud_out || n_out) return gg_get_output(h, slot, index_out, cloud_out, n_out);
-    GG_CUDA(cudaStreamSynchronize(h->streams[0]));
+    GG_CUDA(cudaStreamSynchronize(stream_of(h, slot)));
     return GG_OK;
 }
 
@@ -659,40 +709,56 @@ int gg_filter_cloud_batch(gg_handle h, int count, const gg_scan_desc* scans, con
     if (count <= 0) return GG_OK;
     if (count > h->n_slots) return fail(GG_E_ARG, "count exceeds slots");
     GG_CUDA(cudaSetDevice(h->device));
-    // Groups of scans travel down separate streams so that the H2D copies of one group overlap
-    // the kernels of another and the D2H of a third.  Work enqueued earlier on the primary
-    // stream (map init / roll) must be visible to all of them first.
-    const int groups = std::min(h->n_streams, count);
-    if (groups > 1) {
-        cudaEvent_t ev;
-        GG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        GG_CUDA(cudaEventRecord(ev, h->streams[0]));
-        for (int g = 1; g < groups; ++g) GG_CUDA(cudaStreamWaitEvent(h->streams[g], ev, 0));
-        GG_CUDA(cudaEventDestroy(ev));
+    int rc;
+    // H2D of every cloud on its slot's stream, then the kernels of each stream group, then the
+    // D2H of the labels: copies of one group overlap kernels of the others.
+    for (int i = 0; i < count; ++i) {
+        const gg_scan_desc& d = scans[i];
+        if ((rc = check_slot(h, d.slot))) return rc;
+        if (d.n_points > h->pcap) return fail(GG_E_ARG, "slot %d: too many points", d.slot);
+        if (d.n_points && !points[i]) return fail(GG_E_ARG, "scan %d: null cloud", i);
+        if (d.n_points)
+            GG_CUDA(cudaMemcpyAsync(h->view.points + (size_t)d.slot * h->pcap, points[i], d.n_points * sizeof(gg_point), cudaMemcpyHostToDevice,
+                                    stream_of(h, d.slot)));
     }
-    const int per = (count + groups - 1) / groups;
-    for (int g = 0; g < groups; ++g) {
-        const int b = g * per, e = std::min(count, b + per);
-        if (b >= e) break;
-        cudaStream_t st = h->streams[g];
-        for (int i = b; i < e; ++i) {
-            const gg_scan_desc& d = scans[i];
-            int rc = check_slot(h, d.slot);
-            if (rc) return rc;
-            if (d.n_points > h->pcap) return fail(GG_E_ARG, "slot %d: too many points", d.slot);
-            if (d.n_points)
-                GG_CUDA(cudaMemcpyAsync(h->view.points + (size_t)d.slot * h->pcap, points[i], d.n_points * sizeof(gg_point), cudaMemcpyHostToDevice, st));
-        }
-        int rc = run_scans_on(h, e - b, scans + b, 0, st);
-        if (rc) return rc;
-        if (labels_out)
-            for (int i = b; i < e; ++i)
-                if (labels_out[i] && scans[i].n_points)
-                    GG_CUDA(cudaMemcpyAsync(labels_out[i], h->view.labels + (size_t)scans[i].slot * h->pcap, scans[i].n_points, cudaMemcpyDeviceToHost, st));
-    }
-    for (int g = 0; g < groups; ++g) GG_CUDA(cudaStreamSynchronize(h->streams[g]));
+    if ((rc = run_scans_grouped(h, count, scans, 0))) return rc;
+    if (labels_out)
+        for (int i = 0; i < count; ++i)
+            if (labels_out[i] && scans[i].n_points)
+                GG_CUDA(cudaMemcpyAsync(labels_out[i], h->view.labels + (size_t)scans[i].slot * h->pcap, scans[i].n_points, cudaMemcpyDeviceToHost,
+                                        stream_of(h, scans[i].slot)));
+    return gg_synchronize(h);
+}
+
+// Timing helpers: make every stream wait for the primary one / the primary one for all others,
+// so that a CUDA-event pair on gg_stream() brackets work spread over the handle's streams.
+int gg_fork_streams(gg_handle h) {
+    if (!h) return fail(GG_E_ARG, "null handle");
+    if (h->n_streams <= 1) return GG_OK;
+    GG_CUDA(cudaSetDevice(h->device));
+    cudaEvent_t ev;
+    GG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    GG_CUDA(cudaEventRecord(ev, h->streams[0]));
+    for (int g = 1; g < h->n_streams; ++g) GG_CUDA(cudaStreamWaitEvent(h->streams[g], ev, 0));
+    GG_CUDA(cudaEventDestroy(ev));
     return GG_OK;
 }
+
+int gg_join_streams(gg_handle h) {
+    if (!h) return fail(GG_E_ARG, "null handle");
+    if (h->n_streams <= 1) return GG_OK;
+    GG_CUDA(cudaSetDevice(h->device));
+    for (int g = 1; g < h->n_streams; ++g) {
+        cudaEvent_t ev;
+        GG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        GG_CUDA(cudaEventRecord(ev, h->streams[g]));
+        GG_CUDA(cudaStreamWaitEvent(h->streams[0], ev, 0));
+        GG_CUDA(cudaEventDestroy(ev));
+    }
+    return GG_OK;
+}
+
+int gg_num_streams(gg_handle h) { return h ? h->n_streams : GG_E_ARG; }
 
 int gg_get_layer(gg_handle h, int slot, const char* name, float* dst) {
     int rc = check_slot(h, slot);

@@ -114,6 +114,83 @@ void build_spiral_schedule(int n, std::vector<int>& level_start, std::vector<uin
     for (size_t v = 0; v < seq.size(); ++v) visits[(size_t)cursor[lvl[v]]++] = seq[v];
 }
 
+// Schedule records for the pipelined spiral kernel (k_spiral_pipe): per visit
+//   w0 = x | y << 16
+//   w1, w2 = up to four "recent" entries (16 bit each): bits 14..15 = how many levels earlier
+//            the neighbour was written (1..3, 0 = unused entry), bits 10..13 neighbour index q
+//            (block(q % 3, q / 3) of the 3x3 neighbourhood), bits 0..9 the slot (index inside
+//            its level) of the visit that wrote it
+//   w3 = bit 0: the cell lies beyond minDistSquared (confidence decays, :463-464)
+//        bit 1: second visit of this cell (ring corners are visited twice, :421-438)
+// The kernel prefetches a visit's 3x3 neighbourhood `dist` levels ahead; a neighbour written
+// less than `dist` levels before the visit cannot come from that prefetch and is delivered
+// through shared memory instead.  Returns false if a visit needs more than four such recents
+// or a level has more than 1024 visits (the caller then uses the plain k_spiral).
+bool build_spiral_records(int n, double res_sq, const std::vector<int>& level_start, const std::vector<uint32_t>& visits,
+                          int dist, std::vector<uint32_t>& recs, int& max_recent) {
+    const int c = n / 2 - 1;
+    const size_t nv = visits.size();
+    if (dist < 1 || dist > 3) return false;
+    // level and slot of every visit, looked up by (level-sorted) position
+    std::vector<int> level_of(nv), slot_of(nv);
+    for (size_t l = 0; l + 1 < level_start.size(); ++l) {
+        if (level_start[l + 1] - level_start[l] > 1024) return false;
+        for (int t = level_start[l]; t < level_start[l + 1]; ++t) {
+            level_of[t] = (int)l;
+            slot_of[t] = t - level_start[l];
+        }
+    }
+    // Replay the sequential order to know, for each visit, the last writer of every neighbour.
+    // Sequential order != level-sorted order, so map (cell, occurrence) -> sorted position.
+    std::vector<std::vector<int>> pos_of_cell((size_t)n * n);
+    for (size_t t = 0; t < nv; ++t) {
+        const int x = visits[t] & 0xffff, y = visits[t] >> 16;
+        pos_of_cell[x + (size_t)y * n].push_back((int)t);  // level order == visit order for one cell (WAW)
+    }
+    std::vector<int> seen((size_t)n * n, 0);      // how many visits of the cell happened so far
+    std::vector<int> last_writer((size_t)n * n, -1);  // sorted position of the cell's last writer
+    recs.assign(nv * 4, 0u);
+    max_recent = 0;
+    bool ok = true;
+    auto visit = [&](int x, int y) {
+        const size_t cell = x + (size_t)y * n;
+        const int t = pos_of_cell[cell][seen[cell]];
+        const int lvl = level_of[t];
+        uint32_t r[4] = {0, 0, 0, 0};
+        int nr = 0;
+        for (int q = 0; q < 9; ++q) {
+            const size_t nb = (size_t)(x - 1 + q % 3) + (size_t)(y - 1 + q / 3) * n;
+            const int w = last_writer[nb];
+            if (w >= 0 && level_of[w] < lvl && level_of[w] >= lvl - dist) {
+                // bits 14..15: how many levels earlier the neighbour was written (1 .. dist <= 3); 0 = unused entry
+                if (nr < 4) r[nr] = ((uint32_t)(lvl - level_of[w]) << 14) | ((uint32_t)q << 10) | (uint32_t)slot_of[w];
+                ++nr;
+            } else if (w >= 0 && level_of[w] >= lvl) {
+                ok = false;  // would contradict the levelisation
+            }
+        }
+        if (nr > 4) ok = false;
+        max_recent = std::max(max_recent, nr);
+        const float fx = (float)x - (float)c, fy = (float)y - (float)c;
+        const bool far = ((double)fx * (double)fx + (double)fy * (double)fy) * res_sq > 12.0;
+        recs[4 * (size_t)t + 0] = (uint32_t)x | ((uint32_t)y << 16);
+        recs[4 * (size_t)t + 1] = r[0] | (r[1] << 16);
+        recs[4 * (size_t)t + 2] = r[2] | (r[3] << 16);
+        recs[4 * (size_t)t + 3] = (far ? 1u : 0u) | (seen[cell] ? 2u : 0u);  // bit 1: second visit of a ring corner
+        last_writer[cell] = t;
+        ++seen[cell];
+    };
+    for (int p = c - 1; p >= 1; --p) {
+        const int side = (c - p) * 2;
+        const int q = p + side;
+        for (int pos = p; pos < q; ++pos) visit(p, pos);
+        for (int pos = p; pos < q; ++pos) visit(pos, p);
+        for (int pos = q; pos >= p; --pos) visit(q, pos);
+        for (int pos = q; pos >= p; --pos) visit(pos, q);
+    }
+    return ok;
+}
+
 }  // namespace gg
 
 extern "C" {
@@ -137,6 +214,18 @@ int gg_host_spiral_schedule(int n, int* level_start, int level_cap, uint32_t* vi
     if (level_start && level_cap >= (int)ls.size()) std::memcpy(level_start, ls.data(), ls.size() * sizeof(int));
     if (visits && visit_cap >= (int)vs.size()) std::memcpy(visits, vs.data(), vs.size() * sizeof(uint32_t));
     return 0;
+}
+
+// records of the pipelined spiral kernel: 4 uint32 per visit (see build_spiral_records)
+int gg_host_spiral_records(int n, float resolution, int dist, uint32_t* recs, int rec_cap_words, int* max_recent) {
+    std::vector<int> ls;
+    std::vector<uint32_t> vs, rc;
+    gg::build_spiral_schedule(n, ls, vs);
+    int mr = 0;
+    const bool ok = gg::build_spiral_records(n, (double)resolution * (double)resolution, ls, vs, dist, rc, mr);
+    if (max_recent) *max_recent = mr;
+    if (recs && rec_cap_words >= (int)rc.size()) std::memcpy(recs, rc.data(), rc.size() * sizeof(uint32_t));
+    return ok ? 1 : 0;
 }
 
 int gg_host_move_map(double res, double* pos_xy, double nx, double ny, int* shift_ij) {

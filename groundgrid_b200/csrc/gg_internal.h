@@ -99,6 +99,10 @@ struct View {
     const int* level_start;   // [levels + 1]
     const uint32_t* visits;   // [n_visits]  x | y << 16
     int levels;
+    // pipelined spiral (k_spiral_pipe): 16-byte records, see gg_host.cpp:build_spiral_records
+    const uint4* spiral_recs; // null -> plain k_spiral
+    int spiral_dist;          // prefetch distance the records were built for (1..3)
+    int spiral_threads;       // 512 or 1024 (>= max visits per level)
 
     __host__ __device__ float* layer(int slot, int l) const { return layers + ((size_t)slot * n_layers + l) * k.N2; }
 };

@@ -80,36 +80,49 @@ __device__ __forceinline__ int warp_inclusive_scan(int v) {
     return v;
 }
 
-// Exclusive scan of n ints (in -> out, may alias) by one block of 1024 threads.
-// Returns the grand total to every thread.
+// Exclusive scan of n ints (in -> out, may alias) by one block of 1024 threads: tiles of 4096
+// elements, 4 consecutive ints per thread (coalesced), next tile prefetched while the current
+// one is scanned.  Returns the grand total to every thread.
 __device__ int block_exclusive_scan_1024(const int* in, int* out, int n) {
     __shared__ int s_warp[32];
-    __shared__ int s_total;
+    __shared__ int s_carry;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int per = (n + 1023) / 1024;
-    const int begin = min(tid * per, n), end = min(begin + per, n);
-    int sum = 0;
-    for (int j = begin; j < end; ++j) sum += in[j];
-    const int incl = warp_inclusive_scan(sum);
-    if (lane == 31) s_warp[warp] = incl;
+    if (tid == 0) s_carry = 0;
+    int nx[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) nx[q] = (tid * 4 + q < n) ? in[tid * 4 + q] : 0;
     __syncthreads();
-    if (warp == 0) {
-        const int w = s_warp[lane];
-        const int wi = warp_inclusive_scan(w);
-        s_warp[lane] = wi - w;
-        if (lane == 31) s_total = wi;
+    for (int base = 0; base < n; base += 4096) {
+        int cur[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cur[q] = nx[q];
+        const int nb = base + 4096 + tid * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) nx[q] = (nb + q < n) ? in[nb + q] : 0;
+        const int sum = cur[0] + cur[1] + cur[2] + cur[3];
+        const int incl = warp_inclusive_scan(sum);
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = s_warp[lane];
+            const int wi = warp_inclusive_scan(w);
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        int run = carry + s_warp[warp] + incl - sum;
+        const int idx = base + tid * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (idx + q < n) out[idx + q] = run;
+            run += cur[q];
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = run;
+        __syncthreads();
     }
-    __syncthreads();
-    int run = incl - sum + s_warp[warp];
-    for (int j = begin; j < end; ++j) {
-        const int t = in[j];
-        out[j] = run;
-        run += t;
-    }
-    const int total = s_total;
-    __syncthreads();
-    return total;
+    return s_carry;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -380,21 +393,30 @@ __global__ void __launch_bounds__(128) k_cell_stats(View v, const SlotParams* __
     float n = 0.0f, mean = 0.0f, m2 = 0.0f;
     float mn = FLT_MAX;
     float mx = FLT_MIN, gc = 0.0f, pdm = 0.0f;  // dead layers (FULL only)
-    for (int j = 0; j < cnt; ++j) {
-        const float z = zs[j];
-        const float pd = __fsub_rn(z, oz);  // planeDist, :295
-        if (FULL) gc = (float)__ddiv_rn((double)__fadd_rn(z, __fmul_rn(n, gc)), __dadd_rn((double)n, 1.0));  // :296
-        if (mean == 0.0f) mean = pd;  // :298-299
-        if (!(pd != pd)) {            // :300
-            const float delta = __fsub_rn(pd, mean);
-            mean = __fadd_rn(mean, __fdiv_rn(delta, __fadd_rn(n, 1.0f)));
-            if (FULL) pdm = (float)__ddiv_rn((double)__fadd_rn(pd, __fmul_rn(n, pdm)), __dadd_rn((double)n, 1.0));
-            m2 = __fadd_rn(m2, __fmul_rn(delta, __fsub_rn(pd, mean)));
+    // The recurrence is sequential, the loads are not: fetch up to 8 values at once so that a
+    // heavy cell pays one memory latency per 8 points instead of one per point.
+    for (int j0 = 0; j0 < cnt; j0 += 8) {
+        float zb[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) zb[q] = (j0 + q < cnt) ? zs[j0 + q] : 0.0f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (j0 + q >= cnt) break;
+            const float z = zb[q];
+            const float pd = __fsub_rn(z, oz);  // planeDist, :295
+            if (FULL) gc = (float)__ddiv_rn((double)__fadd_rn(z, __fmul_rn(n, gc)), __dadd_rn((double)n, 1.0));  // :296
+            if (mean == 0.0f) mean = pd;  // :298-299
+            if (!(pd != pd)) {            // :300
+                const float delta = __fsub_rn(pd, mean);
+                mean = __fadd_rn(mean, __fdiv_rn(delta, __fadd_rn(n, 1.0f)));
+                if (FULL) pdm = (float)__ddiv_rn((double)__fadd_rn(pd, __fmul_rn(n, pdm)), __dadd_rn((double)n, 1.0));
+                m2 = __fadd_rn(m2, __fmul_rn(delta, __fsub_rn(pd, mean)));
+            }
+            if (FULL) mx = (mx < z) ? z : mx;                   // std::max(maxHeight, z)
+            const float zl = __fsub_rn(z, 0.0001f);
+            mn = (zl < mn) ? zl : mn;                           // std::min(minHeight, z - 0.0001f)
+            n = __fadd_rn(n, 1.0f);
         }
-        if (FULL) mx = (mx < z) ? z : mx;                   // std::max(maxHeight, z)
-        const float zl = __fsub_rn(z, 0.0001f);
-        mn = (zl < mn) ? zl : mn;                           // std::min(minHeight, z - 0.0001f)
-        n = __fadd_rn(n, 1.0f);
     }
     v.layer(sp.slot, L_COUNT)[cell] = n;
     v.layer(sp.slot, L_VARIANCE)[cell] = __fdiv_rn(m2, __fadd_rn(n, FLT_MIN));
@@ -415,6 +437,13 @@ __global__ void __launch_bounds__(128) k_cell_stats(View v, const SlotParams* __
 constexpr int DT_X = 32, DT_Y = 8, DT_H = 2;
 constexpr int DT_W = DT_X + 2 * DT_H;   // 36
 constexpr int DT_R = DT_Y + 2 * DT_H;   // 12
+
+// confidence decay of interpolate_cell (:464): std::max(c - c / decrease_factor, 0.001) in fp64
+__device__ __forceinline__ float decay_confidence(const Const& k, float occ) {
+    const double o = (double)occ;
+    const double dec = __dsub_rn(o, __ddiv_rn(o, k.dec_factor));
+    return (float)((dec < 0.001) ? 0.001 : dec);
+}
 
 template <int S>
 __device__ __forceinline__ void detect_patch(const Const& k, const float (*sP)[DT_W], const float (*sV)[DT_W], const float (*sM)[DT_W],
@@ -488,17 +517,30 @@ __global__ void __launch_bounds__(DT_X* DT_Y) k_detect(View v, const SlotParams*
     }
     __syncthreads();
     const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
-    if (i < 2 || j < 2 || i >= N - 2 || j >= N - 2) return;  // union of the four sections, :325-328
-    const double di = __dsub_rn((double)i, (double)N / 2.0), dj = __dsub_rn((double)j, (double)N / 2.0);
-    const float sqdist = (float)__dmul_rn(__dadd_rn(__dmul_rn(di, di), __dmul_rn(dj, dj)), k.res_sq);  // :332,356
-    const float e = v.expected[i + j * N];
+    if (i >= N || j >= N) return;
     float* Gp = v.layer(sp.slot, L_GROUND) + i + j * N;
     float* Cp = v.layer(sp.slot, L_GROUNDPATCH) + i + j * N;
-    const int li = threadIdx.x + DT_H, lj = threadIdx.y + DT_H;
-    if ((double)sqdist <= k.psc_sq)
-        detect_patch<3>(k, sP, sV, sM, li, lj, sqdist, e, Gp, Cp);
-    else
-        detect_patch<5>(k, sP, sV, sM, li, lj, sqdist, e, Gp, Cp);
+    if (!(i < 2 || j < 2 || i >= N - 2 || j >= N - 2)) {  // union of the four sections, :325-328
+        const double di = __dsub_rn((double)i, (double)N / 2.0), dj = __dsub_rn((double)j, (double)N / 2.0);
+        const float sqdist = (float)__dmul_rn(__dadd_rn(__dmul_rn(di, di), __dmul_rn(dj, dj)), k.res_sq);  // :332,356
+        const float e = v.expected[i + j * N];
+        const int li = threadIdx.x + DT_H, lj = threadIdx.y + DT_H;
+        if ((double)sqdist <= k.psc_sq)
+            detect_patch<3>(k, sP, sV, sM, li, lj, sqdist, e, Gp, Cp);
+        else
+            detect_patch<5>(k, sP, sV, sM, li, lj, sqdist, e, Gp, Cp);
+    }
+    if (v.spiral_recs) {
+        // Decayed confidence for the spiral sweep, taken off its sequential critical path: the
+        // confidence of a cell only changes at its own visit(s), so decay(C) after patch
+        // detection is exactly what the (first) visit will store; ring corners (i == j) are
+        // visited twice and need the second decay as well.
+        const float cfin = *Cp;
+        const float d1 = decay_confidence(k, cfin);
+        float* D1 = v.roll_scratch + (size_t)sp.slot * 2 * k.N2;
+        D1[i + j * N] = d1;
+        if (i == j) D1[k.N2 + i + j * N] = decay_confidence(k, d1);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -548,6 +590,151 @@ __global__ void __launch_bounds__(SPIRAL_THREADS) k_spiral(View v, const SlotPar
             }
         }
         __syncthreads();
+    }
+}
+
+// Pipelined wavefront.  Same schedule, same arithmetic, but the per-level critical path no
+// longer contains a global-memory round trip:
+//   * schedule records are fetched DIST+1 levels ahead, the 3x3 neighbourhoods of G and C (and
+//     the pre-decayed confidence) DIST levels ahead, so their L2 latency overlaps earlier levels;
+//   * values written fewer than DIST levels before a visit cannot come from that prefetch; the
+//     record names them (neighbour index + producer slot) and they travel through a small
+//     shared-memory ring written by every visit;
+//   * the fp64 confidence decay is read from the table k_detect prepared.
+// Per level: barrier -> <= 3 shared loads -> 9 mul, tree sum, div, 2 mul + add -> stores.
+template <int THREADS, int DIST>
+__global__ void __launch_bounds__(THREADS) k_spiral_pipe(View v, const SlotParams* __restrict__ batch) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    int* s_ls = reinterpret_cast<int*>(s_raw);
+    const int L = v.levels;
+    float2* xch = reinterpret_cast<float2*>(s_raw + (size_t)((L + 4) & ~3) * sizeof(int));  // [DIST + 1][THREADS]
+    const SlotParams& sp = batch[blockIdx.x];
+    const Const& k = v.k;
+    const int N = k.N;
+    const int tid = threadIdx.x;
+    float* G = v.layer(sp.slot, L_GROUND);
+    float* C = v.layer(sp.slot, L_GROUNDPATCH);
+    const float* D1 = v.roll_scratch + (size_t)sp.slot * 2 * k.N2;
+    const float* D2 = D1 + k.N2;
+    const uint4* __restrict__ recs = v.spiral_recs;
+    for (int t = tid; t <= L; t += THREADS) s_ls[t] = v.level_start[t];
+    const int cidx = N / 2 - 1;
+    if (tid == 0) {
+        C[cidx + cidx * N] = 1.0f;          // :405
+        G[cidx + cidx * N] = sp.base_z_f;   // :411
+    }
+    __syncthreads();
+
+    // pipeline state: rec[s] / act[s] describe this thread's visit at level lvl + s
+    uint4 rec[DIST + 1];
+    bool act[DIST + 1];
+    float cc[DIST][9], gg[DIST][9], dd[DIST];
+#pragma unroll
+    for (int s = 0; s <= DIST; ++s) {
+        act[s] = (s < L) && (tid < s_ls[s + 1] - s_ls[s]);
+        rec[s] = act[s] ? recs[s_ls[s] + tid] : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int s = 0; s < DIST; ++s) {
+        dd[s] = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) cc[s][q] = gg[s][q] = 0.0f;
+        if (act[s]) {
+            const int x = (int)(rec[s].x & 0xffffu), y = (int)(rec[s].x >> 16);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const int g = (x - 1 + q % 3) + (y - 1 + q / 3) * N;
+                cc[s][q] = C[g];
+                gg[s][q] = G[g];
+            }
+            dd[s] = (rec[s].w & 2u) ? D2[x + y * N] : D1[x + y * N];
+        }
+    }
+
+    int buf = 0;  // lvl % (DIST + 1)
+    for (int lvl = 0; lvl < L; ++lvl) {
+        // (1) prefetch: neighbourhood of the visit at lvl + DIST, record of lvl + DIST + 1
+        float ncc[9], ngg[9], ndd = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) ncc[q] = ngg[q] = 0.0f;
+        if (act[DIST]) {
+            const int x = (int)(rec[DIST].x & 0xffffu), y = (int)(rec[DIST].x >> 16);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const int g = (x - 1 + q % 3) + (y - 1 + q / 3) * N;
+                ncc[q] = C[g];
+                ngg[q] = G[g];
+            }
+            ndd = (rec[DIST].w & 2u) ? D2[x + y * N] : D1[x + y * N];
+        }
+        uint4 nrec = make_uint4(0, 0, 0, 0);
+        bool nact = false;
+        {
+            const int l2 = lvl + DIST + 1;
+            if (l2 < L) {
+                nact = tid < s_ls[l2 + 1] - s_ls[l2];
+                if (nact) nrec = recs[s_ls[l2] + tid];
+            }
+        }
+        // (2) this level's visit
+        if (act[0]) {
+            const uint32_t ents[4] = {rec[0].y & 0xffffu, rec[0].y >> 16, rec[0].z & 0xffffu, rec[0].z >> 16};
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t e = ents[r];
+                const int back = (int)(e >> 14);  // written `back` levels ago (0: unused entry)
+                if (back) {
+                    int b = buf - back;
+                    if (b < 0) b += DIST + 1;
+                    const float2 val = xch[b * THREADS + (int)(e & 1023u)];
+                    const int q = (int)((e >> 10) & 15u);
+#pragma unroll
+                    for (int qq = 0; qq < 9; ++qq)
+                        if (q == qq) {
+                            gg[0][qq] = val.x;
+                            cc[0][qq] = val.y;
+                        }
+                }
+            }
+            const int x = (int)(rec[0].x & 0xffffu), y = (int)(rec[0].x >> 16);
+            float pr[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) pr[q] = __fmul_rn(cc[0][q], gg[0][q]);
+            const float occ = cc[0][4], h = gg[0][4];
+            const float ssum = __fadd_rn(tree9(cc[0]), FLT_MIN);  // :457
+            const float avg = __fdiv_rn(tree9(pr), ssum);         // :458
+            const float newg = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, occ), avg), __fmul_rn(occ, h));  // :460
+            const bool far = (rec[0].w & 1u) != 0u;               // :463 (geometry only, evaluated on the host)
+            const float newc = far ? dd[0] : occ;                 // :464 (table from k_detect)
+            xch[buf * THREADS + tid] = make_float2(newg, newc);
+            G[x + y * N] = newg;
+            if (far) C[x + y * N] = newc;
+        }
+        __syncthreads();
+        // (3) advance the pipeline by one level
+#pragma unroll
+        for (int s = 0; s + 1 < DIST; ++s) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                cc[s][q] = cc[s + 1][q];
+                gg[s][q] = gg[s + 1][q];
+            }
+            dd[s] = dd[s + 1];
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            cc[DIST - 1][q] = ncc[q];
+            gg[DIST - 1][q] = ngg[q];
+        }
+        dd[DIST - 1] = ndd;
+#pragma unroll
+        for (int s = 0; s < DIST; ++s) {
+            rec[s] = rec[s + 1];
+            act[s] = act[s + 1];
+        }
+        rec[DIST] = nrec;
+        act[DIST] = nact;
+        buf = (buf + 1 == DIST + 1) ? 0 : buf + 1;
     }
 }
 
@@ -736,7 +923,22 @@ int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int 
     ++launches;
     if (stop_after == 2) return launches;
 
-    GG_LAUNCH(K_SPIRAL, k_spiral<<<count, SPIRAL_THREADS, 0, st>>>(v, batch));
+    if (v.spiral_recs) {
+        const size_t shm = (size_t)((v.levels + 4) & ~3) * sizeof(int) + (size_t)(v.spiral_dist + 1) * v.spiral_threads * sizeof(float2);
+#define GG_SPIRAL_CASE(T, D)                                                                      \
+    if (v.spiral_threads == T && v.spiral_dist == D) {                                            \
+        GG_LAUNCH(K_SPIRAL, k_spiral_pipe<T, D><<<count, T, shm, st>>>(v, batch));                \
+    }
+        GG_SPIRAL_CASE(512, 1)
+        GG_SPIRAL_CASE(512, 2)
+        GG_SPIRAL_CASE(512, 3)
+        GG_SPIRAL_CASE(1024, 1)
+        GG_SPIRAL_CASE(1024, 2)
+        GG_SPIRAL_CASE(1024, 3)
+#undef GG_SPIRAL_CASE
+    } else {
+        GG_LAUNCH(K_SPIRAL, k_spiral<<<count, SPIRAL_THREADS, 0, st>>>(v, batch));
+    }
     ++launches;
     if (stop_after == 3) return launches;
 

@@ -1,0 +1,22 @@
+#pragma once
+#include <std_msgs/Header.h>
+#include <vector>
+namespace sensor_msgs {
+struct PointField {
+    enum { INT8 = 1, UINT8 = 2, INT16 = 3, UINT16 = 4, INT32 = 5, UINT32 = 6, FLOAT32 = 7, FLOAT64 = 8 };
+    std::string name;
+    uint32_t offset = 0;
+    uint8_t datatype = 0;
+    uint32_t count = 1;
+};
+struct PointCloud2 {
+    std_msgs::Header header;
+    uint32_t height = 1, width = 0;
+    std::vector<PointField> fields;
+    bool is_bigendian = false;
+    uint32_t point_step = 0, row_step = 0;
+    std::vector<uint8_t> data;
+    bool is_dense = true;
+};
+typedef std::shared_ptr<const PointCloud2> PointCloud2ConstPtr;
+}  // namespace sensor_msgs

@@ -188,8 +188,16 @@ int gg_set_layer(gg_handle h, int slot, const char* name, const float* src);
 int gg_layer_device_ptr(gg_handle h, int slot, const char* name, void** dptr);
 int gg_set_map_position(gg_handle h, int slot, double x, double y);
 
-/* The cudaStream_t the handle enqueues on (primary stream). */
+/* Streams.  Slots are bound to the handle's streams in contiguous groups (GG_STREAMS env,
+ * default 4, capped by n_slots; 1 when the caller supplied a stream) and everything that
+ * touches a slot is enqueued on its stream.  gg_stream() is the primary stream;
+ * gg_fork_streams() makes all streams wait for work already enqueued on it and
+ * gg_join_streams() makes it wait for all others, so an event pair recorded on gg_stream()
+ * around fork ... join brackets the work of every stream. */
 void* gg_stream(gg_handle h);
+int gg_num_streams(gg_handle h);
+int gg_fork_streams(gg_handle h);
+int gg_join_streams(gg_handle h);
 
 /* Counters for bench.py: number of kernel launches issued by this handle so far. */
 uint64_t gg_kernel_launches(gg_handle h);

@@ -147,3 +147,89 @@ def test_spiral_wavefront_schedule_is_exact(dim, res, levels):
     Gs, Cs = run_level_schedule(G, C, 0.3, ls, vs, res)
     assert np.array_equal(o.layer("ground"), Gs)
     assert np.array_equal(o.layer("groundpatch"), Cs)
+
+
+def host_spiral_records(n, res, dist):
+    import ctypes as C
+
+    L = capi.load()
+    L.gg_host_spiral_records.restype = C.c_int
+    L.gg_host_spiral_records.argtypes = [C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    ls, vs = capi.host_spiral_schedule(n)
+    recs = np.zeros(4 * len(vs), np.uint32)
+    mr = C.c_int(0)
+    ok = L.gg_host_spiral_records(n, np.float32(res), dist, recs.ctypes.data_as(C.c_void_p), recs.size, C.byref(mr))
+    return ok, mr.value, ls, recs.reshape(-1, 4)
+
+
+@pytest.mark.parametrize("dist", [1, 2, 3])
+@pytest.mark.parametrize("dim,res", [(33.0, 0.33), (99.0, 0.33)])
+def test_pipelined_spiral_records_emulation(dim, res, dist):
+    """Emulates k_spiral_pipe on the CPU: neighbourhoods are snapshotted `dist` levels before the
+    visit, the entries named by the record come from the exchange ring instead, the decay comes
+    from the table.  Must reproduce the oracle's sequential sweep bit for bit."""
+    o = Oracle(dim, res)
+    n = o.n
+    ok, max_recent, ls, recs = host_spiral_records(n, res, dist)
+    assert ok == 1 and max_recent <= 4
+    L = len(ls) - 1
+    rng = np.random.default_rng(4)
+    o.init_map(0.0, 0.0, 0.0)
+    G = rng.uniform(-1, 1, (n, n)).astype(np.float32)
+    C = (rng.uniform(0, 1, (n, n)) ** 4).astype(np.float32)
+    o.set_layer("ground", G)
+    o.set_layer("groundpatch", C)
+    o.spiral(0.3)
+
+    c = n // 2 - 1
+    G, C = G.copy(), C.copy()
+    o64 = C.astype(np.float64)
+    D1 = np.maximum(o64 - o64 / 5.0, 0.001).astype(np.float32)
+    d64 = D1.astype(np.float64)
+    D2 = np.maximum(d64 - d64 / 5.0, 0.001).astype(np.float32)
+    C[c, c] = 1.0
+    G[c, c] = f32(0.3)
+    ring = {}       # level -> (newg, newc) arrays by slot
+    snaps = {}      # level -> (cc[9], gg[9]) snapshot taken dist levels ahead
+
+    def snapshot(lvl):
+        r = recs[ls[lvl]:ls[lvl + 1]]
+        x, y = (r[:, 0] & 0xFFFF).astype(np.int64), (r[:, 0] >> 16).astype(np.int64)
+        snaps[lvl] = ([C[x - 1 + q % 3, y - 1 + q // 3].copy() for q in range(9)], [G[x - 1 + q % 3, y - 1 + q // 3].copy() for q in range(9)])
+
+    for lvl in range(min(dist, L)):
+        snapshot(lvl)                      # prologue: before level 0 runs
+    for lvl in range(L):
+        if lvl + dist < L:
+            snapshot(lvl + dist)           # prefetch issued at the top of level lvl
+        r = recs[ls[lvl]:ls[lvl + 1]]
+        x, y = (r[:, 0] & 0xFFFF).astype(np.int64), (r[:, 0] >> 16).astype(np.int64)
+        cc, gg = snaps.pop(lvl)
+        ents = np.stack([r[:, 1] & 0xFFFF, r[:, 1] >> 16, r[:, 2] & 0xFFFF, r[:, 2] >> 16], axis=1)
+        for e in ents.T:
+            back = (e >> 14).astype(np.int64)
+            q = ((e >> 10) & 15).astype(np.int64)
+            slot = (e & 1023).astype(np.int64)
+            for b in (1, 2, 3):
+                m = back == b
+                if not m.any():
+                    continue
+                assert b <= dist
+                src_g, src_c = ring[lvl - b]
+                for qq in range(9):
+                    mm = m & (q == qq)
+                    gg[qq][mm] = src_g[slot[mm]]
+                    cc[qq][mm] = src_c[slot[mm]]
+        s = _tree9(cc) + FLT_MIN
+        avg = _tree9([a * b for a, b in zip(cc, gg)]) / s
+        occ = cc[4]
+        newg = (f32(1.0) - occ) * avg + occ * gg[4]
+        far = (r[:, 3] & 1).astype(bool)
+        second = (r[:, 3] & 2).astype(bool)
+        newc = np.where(far, np.where(second, D2[x, y], D1[x, y]), occ).astype(np.float32)
+        ring[lvl] = (newg.copy(), newc.copy())
+        ring.pop(lvl - dist - 1, None)
+        G[x, y] = newg
+        C[x[far], y[far]] = newc[far]
+    assert np.array_equal(o.layer("ground"), G)
+    assert np.array_equal(o.layer("groundpatch"), C)
