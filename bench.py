@@ -369,12 +369,14 @@ def main():
         for _ in range(args.steps):
             s = step_e2e()
             pts_e2e += int(pts_per_pose[s])
-            h2d = int(pts_per_pose[s]) * 32
+            h2d = int(pts_per_pose[s]) * (14 if g.host_pack_threads else 32)
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": sum_over_ranks(pts_e2e) / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(h2d)),
                "d2h_bytes_per_step": int(sum_over_ranks(int(pts_per_pose.max()))), "ms_per_step": dt / args.steps * 1e3,
-               "api": "gg_update_pose_batch + gg_filter_cloud_batch (pinned host clouds in, labels out)"}
+               "api": "gg_update_pose_batch + gg_filter_cloud_batch (pinned host PointXYZIR clouds in, labels out)",
+               "host_pack_threads": g.host_pack_threads,
+               "pcie_bytes_per_point": 14 if g.host_pack_threads else 32}
 
     # ---- roofline of the dominant kernel (CUDA events around every launch, same timed region)
     P_mean = float(npts.mean())

@@ -103,6 +103,7 @@ def load(build_if_missing=True):
         "gg_layer_device_ptr": (i, [vp, i, C.c_char_p, C.POINTER(vp)]),
         "gg_stream": (vp, [vp]),
         "gg_num_streams": (i, [vp]),
+        "gg_host_pack_threads": (i, [vp]),
         "gg_fork_streams": (i, [vp]),
         "gg_join_streams": (i, [vp]),
         "gg_kernel_launches": (C.c_uint64, [vp]),
@@ -244,6 +245,10 @@ class GroundGridB200:
     @property
     def n_streams(self):
         return self._l.gg_num_streams(self._h)
+
+    @property
+    def host_pack_threads(self):
+        return self._l.gg_host_pack_threads(self._h)
 
     def fork_streams(self):
         _check(self._l.gg_fork_streams(self._h))

@@ -6,9 +6,13 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <atomic>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "gg_host.h"
@@ -94,6 +98,101 @@ struct EventProfiler : gg::Profiler {
     Rec* cur = nullptr;
 };
 
+// Host-side packing of PointXYZIR clouds for the batched host-buffer path: the 32-byte records
+// carry 14 useful bytes (x, y, z, ring); PCIe is the bottleneck of that path, so worker threads
+// repack every cloud into pinned staging memory as x | y | z (float[n_pad]) | ring (u16[n_pad]), n_pad = n rounded up to 8,
+// with streaming stores, and only 14 bytes per point cross the bus.
+struct PackJob {
+    const gg_point* src = nullptr;
+    size_t n = 0;
+    unsigned char* dst = nullptr;
+    std::atomic<int> remaining{0};
+};
+
+class HostPacker {
+  public:
+    static constexpr size_t kChunk = 16384;  // points per work item (multiple of 8)
+    explicit HostPacker(int threads) {
+        for (int t = 0; t < threads; ++t) workers_.emplace_back([this] { loop(); });
+    }
+    ~HostPacker() {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            stop_ = true;
+            ++epoch_;
+        }
+        cv_.notify_all();
+        for (auto& w : workers_) w.join();
+    }
+    int threads() const { return (int)workers_.size(); }
+
+    // jobs must stay alive until wait_all(); chunks are handed out in job order
+    void start(std::vector<PackJob>* jobs) {
+        while (busy_.load(std::memory_order_acquire) != 0) std::this_thread::yield();  // stragglers of the previous run
+        chunks_.clear();
+        for (size_t j = 0; j < jobs->size(); ++j) {
+            PackJob& job = (*jobs)[j];
+            const int nch = (int)std::max<size_t>(1, (job.n + kChunk - 1) / kChunk);
+            job.remaining.store(nch, std::memory_order_relaxed);
+            for (int c = 0; c < nch; ++c) chunks_.push_back({(int)j, c});
+        }
+        next_.store(0, std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            jobs_ = jobs;
+            ++epoch_;
+        }
+        cv_.notify_all();
+    }
+    // the calling thread helps until the job is packed
+    void wait_job(PackJob& job) {
+        while (job.remaining.load(std::memory_order_acquire) > 0) {
+            if (!work_one()) std::this_thread::yield();
+        }
+    }
+
+    static void pack_range(const gg_point* src, size_t n, unsigned char* dst, size_t i0, size_t i1) {
+        gg::pack_cloud_range(src, n, dst, i0, i1);
+    }
+
+  private:
+    bool work_one() {
+        std::vector<PackJob>* jobs = jobs_;
+        if (!jobs) return false;
+        const size_t c = next_.fetch_add(1, std::memory_order_relaxed);
+        if (c >= chunks_.size()) return false;
+        PackJob& job = (*jobs)[chunks_[c].first];
+        const size_t i0 = (size_t)chunks_[c].second * kChunk;
+        pack_range(job.src, job.n, job.dst, i0, std::min(job.n, i0 + kChunk));
+        job.remaining.fetch_sub(1, std::memory_order_release);
+        return true;
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                cv_.wait(g, [&] { return epoch_ != seen; });
+                seen = epoch_;
+                if (stop_) return;
+                busy_.fetch_add(1, std::memory_order_acq_rel);
+            }
+            while (work_one()) {
+            }
+            busy_.fetch_sub(1, std::memory_order_acq_rel);
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::vector<PackJob>* jobs_ = nullptr;
+    std::vector<std::pair<int, int>> chunks_;
+    std::atomic<size_t> next_{0};
+    std::atomic<int> busy_{0};
+    uint64_t epoch_ = 0;
+    bool stop_ = false;
+};
+
 struct SlotState {
     bool have_map = false;
     double px = 0.0, py = 0.0;
@@ -102,6 +201,7 @@ struct SlotState {
     bool ran = false;
     bool output_valid = false;
     const gg_point* src = nullptr;  // caller-owned device cloud of the last scan (null: the slot's own buffer)
+    bool packed_input = false;      // last scan came through the packed host path (no 32-byte records on the device)
 };
 
 }  // namespace
@@ -129,6 +229,9 @@ struct gg_handle_s {
     std::vector<void*> dev_allocs;
     int sched_levels = 0, sched_visits = 0, sched_max = 0;
     bool out_cloud_ready = false;
+    HostPacker* packer = nullptr;    // created on the first packed batch call
+    unsigned char* h_packed = nullptr;  // pinned staging, [n_slots][14 * pcap]
+    int host_pack = 1;               // GG_HOST_PACK=0 sends the 32-byte records as they are
     EventProfiler* prof = nullptr;   // non-null while profiling is enabled
     double prof_ms[gg::K_NUM] = {};
     uint32_t prof_count[gg::K_NUM] = {};
@@ -214,7 +317,7 @@ int ring_release(gg_handle h, int pos, cudaStream_t st) {
 int stream_index(gg_handle h, int slot) { return (int)((long long)slot * h->n_streams / h->n_slots); }
 cudaStream_t stream_of(gg_handle h, int slot) { return h->streams[stream_index(h, slot)]; }
 
-void fill_params(gg_handle h, const gg_scan_desc& d, gg::SlotParams& p, const gg_point* src) {
+void fill_params(gg_handle h, const gg_scan_desc& d, gg::SlotParams& p, const gg_point* src, const float* packed = nullptr) {
     const SlotState& s = h->slots[d.slot];
     std::memset(&p, 0, sizeof(p));
     p.px = s.px;
@@ -226,10 +329,12 @@ void fill_params(gg_handle h, const gg_scan_desc& d, gg::SlotParams& p, const gg
     p.n_points = (int)d.n_points;
     p.slot = d.slot;
     p.src = src ? src : h->view.points + (size_t)d.slot * h->pcap;
+    p.packed = packed;
 }
 
 // enqueue the kernels of `count` scans, each group of slots on its own stream
-int run_scans_grouped(gg_handle h, int count, const gg_scan_desc* scans, int stop_after, const gg_point* const* dev_points = nullptr) {
+int run_scans_grouped(gg_handle h, int count, const gg_scan_desc* scans, int stop_after, const gg_point* const* dev_points = nullptr,
+                      bool packed = false, int only_group = -1) {
     if (count <= 0) return GG_OK;
     if (count > h->n_slots) return fail(GG_E_ARG, "count %d exceeds the number of slots %d", count, h->n_slots);
     int rc;
@@ -240,13 +345,15 @@ int run_scans_grouped(gg_handle h, int count, const gg_scan_desc* scans, int sto
         if (d.n_points > h->pcap) return fail(GG_E_ARG, "slot %d: %zu points exceed capacity %zu", d.slot, d.n_points, h->pcap);
     }
     for (int g = 0; g < h->n_streams; ++g) {
+        if (only_group >= 0 && g != only_group) continue;
         gg::SlotParams *hp = nullptr, *dp = nullptr;
         int pos = 0, m = 0, max_points = 0;
         for (int i = 0; i < count; ++i) {
             const gg_scan_desc& d = scans[i];
             if (stream_index(h, d.slot) != g) continue;
             if (m == 0 && (rc = ring_acquire(h, &hp, &dp, &pos))) return rc;
-            fill_params(h, d, hp[m], dev_points ? dev_points[i] : nullptr);
+            fill_params(h, d, hp[m], dev_points ? dev_points[i] : nullptr,
+                        packed ? reinterpret_cast<const float*>(h->view.packed + (size_t)d.slot * 14 * h->pcap) : nullptr);
             ++m;
             max_points = std::max(max_points, (int)d.n_points);
             SlotState& s = h->slots[d.slot];
@@ -255,6 +362,7 @@ int run_scans_grouped(gg_handle h, int count, const gg_scan_desc* scans, int sto
             s.ran = true;
             s.output_valid = false;
             s.src = dev_points ? dev_points[i] : nullptr;
+            s.packed_input = packed;
         }
         if (m == 0) continue;
         cudaStream_t st = h->streams[g];
@@ -277,6 +385,8 @@ int ensure_out_cloud(gg_handle h) {
 int run_output_on(gg_handle h, int slot, bool want_cloud, cudaStream_t st) {
     SlotState& s = h->slots[slot];
     if (!s.ran || s.last_stop != 0) return fail(GG_E_STATE, "slot %d: no completed scan", slot);
+    if (want_cloud && s.packed_input)
+        return fail(GG_E_STATE, "slot %d: the output cloud needs the 32-byte records on the device (use gg_filter_cloud or GG_HOST_PACK=0)", slot);
     int rc;
     if (want_cloud && (rc = ensure_out_cloud(h))) return rc;
     gg::SlotParams *hp = nullptr, *dp = nullptr;
@@ -441,6 +551,8 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
         }
     }
 
+    if (const char* e = getenv("GG_HOST_PACK")) h->host_pack = atoi(e) ? 1 : 0;
+    v.packed = nullptr;
     if (stream) {
         h->own_streams = false;
         h->n_streams = 1;
@@ -465,6 +577,8 @@ int gg_destroy(gg_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     delete h->prof;
+    delete h->packer;
+    if (h->h_packed) cudaFreeHost(h->h_packed);
     for (void* p : h->dev_allocs) cudaFree(p);
     if (h->h_ring) cudaFreeHost(h->h_ring);
     for (int i = 0; i < kRing; ++i)
@@ -710,18 +824,67 @@ int gg_filter_cloud_batch(gg_handle h, int count, const gg_scan_desc* scans, con
     if (count > h->n_slots) return fail(GG_E_ARG, "count exceeds slots");
     GG_CUDA(cudaSetDevice(h->device));
     int rc;
-    // H2D of every cloud on its slot's stream, then the kernels of each stream group, then the
-    // D2H of the labels: copies of one group overlap kernels of the others.
     for (int i = 0; i < count; ++i) {
         const gg_scan_desc& d = scans[i];
         if ((rc = check_slot(h, d.slot))) return rc;
         if (d.n_points > h->pcap) return fail(GG_E_ARG, "slot %d: too many points", d.slot);
         if (d.n_points && !points[i]) return fail(GG_E_ARG, "scan %d: null cloud", i);
-        if (d.n_points)
-            GG_CUDA(cudaMemcpyAsync(h->view.points + (size_t)d.slot * h->pcap, points[i], d.n_points * sizeof(gg_point), cudaMemcpyHostToDevice,
-                                    stream_of(h, d.slot)));
     }
-    if ((rc = run_scans_grouped(h, count, scans, 0))) return rc;
+    if (h->host_pack && !h->packer) {
+        // packing pays only with enough host threads; with few (e.g. 8 ranks sharing a small CPU
+        // quota) the plain 32-byte DMA is faster.  GG_HOST_THREADS forces a count.
+        int threads = 0;
+        if (const char* e = getenv("GG_HOST_THREADS")) threads = atoi(e);
+        if (threads <= 0) {
+            int local = 1;
+            if (const char* e = getenv("LOCAL_WORLD_SIZE")) local = std::max(1, atoi(e));
+            threads = std::min(48, gg::usable_cpus() / local - 1);
+            if (threads < 6) h->host_pack = 0;
+        }
+        if (h->host_pack) h->packer = new HostPacker(std::max(1, threads));
+    }
+    if (h->host_pack) {
+        // Packed path: worker threads repack the clouds (14 useful bytes of every 32-byte record)
+        // into pinned staging memory, group by group; as soon as a cloud is packed its H2D copy is
+        // enqueued, and as soon as a stream group is complete its kernels are launched, so packing,
+        // PCIe traffic and kernels of different groups overlap.
+        if (!h->h_packed) {
+            GG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->h_packed), (size_t)h->n_slots * 14 * h->pcap, cudaHostAllocDefault));
+            if ((rc = dev_alloc(h, &h->view.packed, (size_t)h->n_slots * 14 * h->pcap))) return rc;
+        }
+        std::vector<int> order;
+        for (int g = 0; g < h->n_streams; ++g)
+            for (int i = 0; i < count; ++i)
+                if (stream_index(h, scans[i].slot) == g) order.push_back(i);
+        std::vector<PackJob> jobs(count);
+        for (int k = 0; k < count; ++k) {
+            const gg_scan_desc& d = scans[order[k]];
+            jobs[k].src = points[order[k]];
+            jobs[k].n = d.n_points;
+            jobs[k].dst = h->h_packed + (size_t)d.slot * 14 * h->pcap;
+        }
+        h->packer->start(&jobs);
+        for (int k = 0; k < count; ++k) {
+            const gg_scan_desc& d = scans[order[k]];
+            h->packer->wait_job(jobs[k]);
+            const size_t n_pad = (d.n_points + 7) & ~(size_t)7;
+            if (d.n_points)
+                GG_CUDA(cudaMemcpyAsync(h->view.packed + (size_t)d.slot * 14 * h->pcap, jobs[k].dst, 14 * n_pad, cudaMemcpyHostToDevice,
+                                        stream_of(h, d.slot)));
+            const int g = stream_index(h, d.slot);
+            if (k + 1 == count || stream_index(h, scans[order[k + 1]].slot) != g)
+                if ((rc = run_scans_grouped(h, count, scans, 0, nullptr, true, g))) return rc;
+        }
+    } else {
+        // H2D of every 32-byte cloud on its slot's stream, then the kernels of each stream group
+        for (int i = 0; i < count; ++i) {
+            const gg_scan_desc& d = scans[i];
+            if (d.n_points)
+                GG_CUDA(cudaMemcpyAsync(h->view.points + (size_t)d.slot * h->pcap, points[i], d.n_points * sizeof(gg_point), cudaMemcpyHostToDevice,
+                                        stream_of(h, d.slot)));
+        }
+        if ((rc = run_scans_grouped(h, count, scans, 0))) return rc;
+    }
     if (labels_out)
         for (int i = 0; i < count; ++i)
             if (labels_out[i] && scans[i].n_points)
@@ -759,6 +922,22 @@ int gg_join_streams(gg_handle h) {
 }
 
 int gg_num_streams(gg_handle h) { return h ? h->n_streams : GG_E_ARG; }
+
+// host-only: the repacking of gg_filter_cloud_batch for one cloud (dst: 14 * ((n + 7) & ~7) bytes,
+// 32-byte aligned), chunked like the worker threads do it -- exported for the CPU tests
+int gg_host_pack_cloud(const gg_point* src, size_t n, unsigned char* dst) {
+    if ((!src && n) || !dst) return GG_E_ARG;
+    size_t i0 = 0;
+    do {
+        const size_t i1 = std::min(n, i0 + HostPacker::kChunk);
+        HostPacker::pack_range(src, n, dst, i0, i1);
+        i0 = i1;
+    } while (i0 < n);
+    return GG_OK;
+}
+
+// number of host threads that repack clouds in gg_filter_cloud_batch (0: packing disabled or not used yet)
+int gg_host_pack_threads(gg_handle h) { return (h && h->host_pack && h->packer) ? h->packer->threads() + 1 : 0; }
 
 int gg_get_layer(gg_handle h, int slot, const char* name, float* dst) {
     int rc = check_slot(h, slot);

@@ -1,11 +1,17 @@
 // Host-side (no CUDA) pieces of the library: expectedPoints table, config-derived constants,
 // the map-move arithmetic and the wavefront schedule of the spiral interpolation.  They are
 // exported with a gg_host_ prefix so the CPU test-suite can exercise them without a GPU.
+#include <immintrin.h>
+
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <thread>
 #include <cstdint>
 #include <cstring>
 #include <vector>
+
+#include <sched.h>
 
 #include "gg_host.h"
 
@@ -189,6 +195,113 @@ bool build_spiral_records(int n, double res_sq, const std::vector<int>& level_st
         for (int pos = q; pos >= p; --pos) visit(pos, q);
     }
     return ok;
+}
+
+// ---- host-side cloud packing (gg_filter_cloud_batch) -------------------------------------
+// PointXYZIR records (32 B, 14 useful) -> x | y | z (float[n_pad]) | ring (u16[n_pad]) with
+// n_pad = n rounded up to 8, written with streaming stores into pinned staging memory.
+// [i0, i1) is a chunk: i0 a multiple of 8, i1 == n for the last chunk (which also zero-fills
+// the padding).  AVX2 variant selected at run time.
+static void pack_tail(const gg_point* src, size_t n, size_t n_pad, float* x, float* y, float* z, uint16_t* r, size_t i, size_t i1) {
+    for (; i < i1 && i < n; ++i) {
+        x[i] = src[i].x;
+        y[i] = src[i].y;
+        z[i] = src[i].z;
+        r[i] = src[i].ring;
+    }
+    if (i1 >= n)
+        for (size_t t = n; t < n_pad; ++t) {
+            x[t] = y[t] = z[t] = 0.f;
+            r[t] = 0;
+        }
+}
+
+static void pack_sse2(const gg_point* src, size_t n, unsigned char* dst, size_t i0, size_t i1) {
+    const size_t n_pad = (n + 7) & ~(size_t)7;
+    float* x = reinterpret_cast<float*>(dst);
+    float* y = x + n_pad;
+    float* z = y + n_pad;
+    uint16_t* r = reinterpret_cast<uint16_t*>(z + n_pad);
+    size_t i = i0;
+    const size_t vec_end = i0 + ((std::min(i1, n) - i0) & ~(size_t)7);
+    for (; i < vec_end; i += 8) {
+        alignas(16) uint16_t rr[8];
+        for (int h = 0; h < 2; ++h) {
+            const gg_point* p = src + i + 4 * h;
+            __m128 a = _mm_loadu_ps(&p[0].x), b = _mm_loadu_ps(&p[1].x), c = _mm_loadu_ps(&p[2].x), d = _mm_loadu_ps(&p[3].x);
+            _MM_TRANSPOSE4_PS(a, b, c, d);  // a = x0..x3, b = y0..y3, c = z0..z3
+            _mm_stream_ps(x + i + 4 * h, a);
+            _mm_stream_ps(y + i + 4 * h, b);
+            _mm_stream_ps(z + i + 4 * h, c);
+            for (int q = 0; q < 4; ++q) rr[4 * h + q] = p[q].ring;
+        }
+        _mm_stream_si128(reinterpret_cast<__m128i*>(r + i), _mm_load_si128(reinterpret_cast<const __m128i*>(rr)));
+    }
+    pack_tail(src, n, n_pad, x, y, z, r, i, i1);
+    _mm_sfence();
+}
+
+__attribute__((target("avx2"))) static void pack_avx2(const gg_point* src, size_t n, unsigned char* dst, size_t i0, size_t i1) {
+    const size_t n_pad = (n + 7) & ~(size_t)7;
+    float* x = reinterpret_cast<float*>(dst);
+    float* y = x + n_pad;
+    float* z = y + n_pad;
+    uint16_t* r = reinterpret_cast<uint16_t*>(z + n_pad);
+    size_t i = i0;
+    const size_t vec_end = i0 + ((std::min(i1, n) - i0) & ~(size_t)7);
+    for (; i < vec_end; i += 8) {
+        const gg_point* p = src + i;
+        _mm_prefetch(reinterpret_cast<const char*>(p + 32), _MM_HINT_NTA);
+        _mm_prefetch(reinterpret_cast<const char*>(p + 34), _MM_HINT_NTA);
+        _mm_prefetch(reinterpret_cast<const char*>(p + 36), _MM_HINT_NTA);
+        _mm_prefetch(reinterpret_cast<const char*>(p + 38), _MM_HINT_NTA);
+        // lane 0: records 0..3, lane 1: records 4..7; transpose 4x4 inside each 128-bit lane
+        const __m256 a = _mm256_loadu2_m128(&p[4].x, &p[0].x), b = _mm256_loadu2_m128(&p[5].x, &p[1].x);
+        const __m256 c = _mm256_loadu2_m128(&p[6].x, &p[2].x), d = _mm256_loadu2_m128(&p[7].x, &p[3].x);
+        const __m256 t0 = _mm256_unpacklo_ps(a, b), t1 = _mm256_unpackhi_ps(a, b);
+        const __m256 t2 = _mm256_unpacklo_ps(c, d), t3 = _mm256_unpackhi_ps(c, d);
+        _mm256_stream_ps(x + i, _mm256_shuffle_ps(t0, t2, 0x44));  // x0..x3 | x4..x7
+        _mm256_stream_ps(y + i, _mm256_shuffle_ps(t0, t2, 0xEE));
+        _mm256_stream_ps(z + i, _mm256_shuffle_ps(t1, t3, 0x44));
+        alignas(16) uint16_t rr[8];
+        for (int q = 0; q < 8; ++q) rr[q] = p[q].ring;
+        _mm_stream_si128(reinterpret_cast<__m128i*>(r + i), _mm_load_si128(reinterpret_cast<const __m128i*>(rr)));
+    }
+    pack_tail(src, n, n_pad, x, y, z, r, i, i1);
+    _mm_sfence();
+}
+
+void pack_cloud_range(const gg_point* src, size_t n, unsigned char* dst, size_t i0, size_t i1) {
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0)
+        pack_avx2(src, n, dst, i0, i1);
+    else
+        pack_sse2(src, n, dst, i0, i1);
+}
+
+// CPUs this process may actually use: affinity mask capped by the cgroup CPU quota
+int usable_cpus() {
+    int n = (int)std::thread::hardware_concurrency();
+#ifdef __linux__
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = std::min(n, CPU_COUNT(&set));
+    if (FILE* f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char quota[32];
+        long period = 0;
+        if (std::fscanf(f, "%31s %ld", quota, &period) == 2 && period > 0 && quota[0] != 'm') n = std::min(n, (int)std::max(1L, std::atol(quota) / period));
+        std::fclose(f);
+    } else if (FILE* f1 = std::fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) {
+        long q = -1, per = 100000;
+        if (std::fscanf(f1, "%ld", &q) != 1) q = -1;
+        std::fclose(f1);
+        if (FILE* f2 = std::fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) {
+            if (std::fscanf(f2, "%ld", &per) != 1) per = 100000;
+            std::fclose(f2);
+        }
+        if (q > 0 && per > 0) n = std::min(n, (int)std::max(1L, q / per));
+    }
+#endif
+    return std::max(1, n);
 }
 
 }  // namespace gg

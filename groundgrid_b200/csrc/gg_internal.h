@@ -66,6 +66,9 @@ struct SlotParams {
     int shift_i, shift_j; // pending roll (index shift): new(r,c) = old(r + shift_i, c + shift_j)
     int slot;
     const gg_point* src;  // device pointer of this scan's cloud (the slot's own buffer or a caller-owned one)
+    // packed cloud (host-side packing of the batched host-buffer path): x | y | z as float[n_pad]
+    // followed by ring as uint16[n_pad], n_pad = n_points rounded up to 8; null -> `src` is used
+    const float* packed;
 };
 
 // Pointers / strides of the handle's device arena, passed to kernels by value.
@@ -75,6 +78,7 @@ struct View {
     int n_layers;
     const float* expected;  // [N2] expectedPoints table (GroundSegmentation.cpp:40-46)
     gg_point* points;     // [n_slots][pcap]
+    unsigned char* packed;  // [n_slots][14 * pcap] packed clouds (allocated on first use)
     uint32_t* key;        // [n_slots][pcap] cell index of kept points, N2 for everything else
     uint32_t* key2;       // sort ping-pong
     float* zval;          // [n_slots][pcap] z per input point

@@ -195,12 +195,23 @@ __global__ void __launch_bounds__(256) k_rasterize(View v, const SlotParams* __r
     const int N = k.N;
     const size_t base = (size_t)sp.slot * v.pcap;
 
-    // coalesced 2 x 16-byte loads of the 32-byte PointXYZIR record
-    const uint4* rec = reinterpret_cast<const uint4*>(sp.src + i);
-    const uint4 a = __ldg(rec);
-    const uint4 b = __ldg(rec + 1);
-    const float x = __uint_as_float(a.x), y = __uint_as_float(a.y), z = __uint_as_float(a.z);
-    const int ring = (int)(b.y & 0xffffu);
+    float x, y, z;
+    int ring;
+    if (sp.packed) {
+        // packed SoA cloud: four fully coalesced streams, 14 bytes per point
+        const int n_pad = (sp.n_points + 7) & ~7;
+        x = __ldg(sp.packed + i);
+        y = __ldg(sp.packed + n_pad + i);
+        z = __ldg(sp.packed + 2 * n_pad + i);
+        ring = (int)__ldg(reinterpret_cast<const unsigned short*>(sp.packed + 3 * n_pad) + i);
+    } else {
+        // coalesced 2 x 16-byte loads of the 32-byte PointXYZIR record
+        const uint4* rec = reinterpret_cast<const uint4*>(sp.src + i);
+        const uint4 a = __ldg(rec);
+        const uint4 b = __ldg(rec + 1);
+        x = __uint_as_float(a.x), y = __uint_as_float(a.y), z = __uint_as_float(a.z);
+        ring = (int)(b.y & 0xffffu);
+    }
     const float ox = sp.ox, oy = sp.oy, oz = sp.oz;
 
     const float dxo = __fsub_rn(x, ox), dyo = __fsub_rn(y, oy);

@@ -142,7 +142,11 @@ int gg_filter_cloud(gg_handle h, int slot, const gg_point* points, size_t n, con
 
 /* Batched form of gg_filter_cloud: `count` independent scans (distinct slots), host buffers.
  * points[k] / labels_out[k] are per-scan host pointers (pinned memory makes the copies
- * asynchronous).  Copies and kernels of different scans overlap on internal streams. */
+ * asynchronous).  Copies and kernels of different scans overlap on internal streams.
+ * PCIe is the bottleneck of this path, so by default (GG_HOST_PACK=1) host worker threads
+ * (GG_HOST_THREADS) first repack every cloud into pinned staging memory as
+ * x | y | z | ring (14 of the 32 bytes of a PointXYZIR record are used by the algorithm) and
+ * only those bytes cross the bus; results are identical. */
 int gg_filter_cloud_batch(gg_handle h, int count, const gg_scan_desc* scans, const gg_point* const* points,
                           uint8_t* const* labels_out);
 
@@ -196,6 +200,7 @@ int gg_set_map_position(gg_handle h, int slot, double x, double y);
  * around fork ... join brackets the work of every stream. */
 void* gg_stream(gg_handle h);
 int gg_num_streams(gg_handle h);
+int gg_host_pack_threads(gg_handle h);
 int gg_fork_streams(gg_handle h);
 int gg_join_streams(gg_handle h);
 

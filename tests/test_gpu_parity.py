@@ -284,6 +284,33 @@ def test_batched_slots_match_single_and_are_deterministic():
         assert np.array_equal(g2.layer("ground", slot=b), g.layer("ground", slot=b))
 
 
+def test_batch_path_with_and_without_host_packing(monkeypatch):
+    import torch
+
+    dim, res, B = 99.0, 0.33, 3
+    scans = [synth.scan_64(synth.make_scene(seed=300 + b), seed=300 + b) for b in range(B)]
+    hp = [torch.from_numpy(np.ascontiguousarray(p).view(np.uint8).copy()).pin_memory() for p, _ in scans]
+    out = {}
+    for pack in ("1", "0"):
+        monkeypatch.setenv("GG_HOST_PACK", pack)
+        g = capi.GroundGridB200(dim, res, n_slots=B, max_points=131072)
+        hl = [torch.zeros(len(p), dtype=torch.uint8).pin_memory() for p, _ in scans]
+        for b in range(B):
+            g.init_map(0.0, 0.0, 0.0, slot=b)
+        for rep in range(2):
+            descs = g.make_descs(list(range(B)), [len(p) for p, _ in scans], [o for _, o in scans], [0.0] * B)
+            g.filter_cloud_batch_ptrs(descs, [t.data_ptr() for t in hp], [t.data_ptr() for t in hl])
+        assert (g.host_pack_threads > 0) == (pack == "1")
+        out[pack] = [t.numpy().copy() for t in hl]
+        g.close()
+    for b in range(B):
+        o = Oracle(dim, res)
+        o.init_map(0.0, 0.0, 0.0)
+        for rep in range(2):
+            want, _, _ = o.filter_cloud(scans[b][0], scans[b][1], 0.0, threads=1)
+        assert np.array_equal(out["1"][b], want) and np.array_equal(out["0"][b], want)
+
+
 def test_error_codes():
     g = capi.GroundGridB200(33.0, 0.33, n_slots=2, max_points=1024)
     org = np.zeros(3, np.float32)

@@ -233,3 +233,31 @@ def test_pipelined_spiral_records_emulation(dim, res, dist):
         C[x[far], y[far]] = newc[far]
     assert np.array_equal(o.layer("ground"), G)
     assert np.array_equal(o.layer("groundpatch"), C)
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 16383, 16384, 16385, 40001])
+def test_host_cloud_packing(n):
+    """gg_filter_cloud_batch repacks PointXYZIR records as x | y | z | ring before the H2D copy."""
+    import ctypes as C
+
+    from groundgrid_b200 import synth
+
+    rng = np.random.default_rng(n)
+    pts = np.zeros(n, synth.POINT_DTYPE)
+    for c in "xyz":
+        pts[c] = rng.standard_normal(n).astype(np.float32)
+    pts["intensity"] = 7.0
+    pts["ring"] = rng.integers(0, 65535, n)
+    n_pad = (n + 7) & ~7
+    raw = np.full(14 * n_pad + 64, 0xAB, np.uint8)
+    off = (-raw.ctypes.data) % 32
+    dst = raw[off:off + 14 * n_pad]
+    L = capi.load()
+    L.gg_host_pack_cloud.restype = C.c_int
+    L.gg_host_pack_cloud.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    assert L.gg_host_pack_cloud(pts.ctypes.data_as(C.c_void_p), n, dst.ctypes.data_as(C.c_void_p)) == 0
+    f = dst[:12 * n_pad].view(np.float32)
+    assert np.array_equal(f[:n], pts["x"]) and np.array_equal(f[n_pad:n_pad + n], pts["y"]) and np.array_equal(f[2 * n_pad:2 * n_pad + n], pts["z"])
+    assert np.array_equal(dst[12 * n_pad:].view(np.uint16)[:n], pts["ring"])
+    assert np.all(f[n:n_pad] == 0) and np.all(dst[12 * n_pad:].view(np.uint16)[n:] == 0)
+    assert np.all(raw[off + 14 * n_pad:] == 0xAB)
