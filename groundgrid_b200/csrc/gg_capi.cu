@@ -549,6 +549,70 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
             v.spiral_recs = reinterpret_cast<const uint4*>(d_rc);
             v.spiral_dist = dist;
         }
+        // skewed-layout spiral (GG_SPIRAL_SKEW=0 keeps the pipelined kernel); needs 4 * KP + 32 <= 1024 threads
+        std::memset(&v.skew, 0, sizeof(v.skew));
+        int want_skew = 1;
+        if (const char* e = getenv("GG_SPIRAL_SKEW")) want_skew = atoi(e);
+        gg::SkewTables sk;
+        if (want_skew) gg::build_spiral_skew(n, ls, vs, sk);
+        if (sk.ok && sk.max_irr_per_level * 9 <= 64 && sk.lanes + 64 <= 1024) {
+            // re-layout of the irregular records: one dense block per level (see SkewView)
+            const int irr_max = std::max(1, sk.max_irr_per_level);
+            const int irr_words = ((irr_max * 22 + 3) / 4) * 4;
+            std::vector<uint32_t> blocks((size_t)(sk.levels + 4) * irr_words, 0xffffffffu);
+            for (int l = 0; l < sk.levels; ++l)
+                for (int r = sk.irr_level_start[l]; r < sk.irr_level_start[l + 1]; ++r) {
+                    const uint32_t* w = &sk.irr_recs[(size_t)r * 16];
+                    const int vv = r - sk.irr_level_start[l];
+                    uint32_t* blk = &blocks[(size_t)l * irr_words];
+                    for (int q = 0; q < 9; ++q) {
+                        blk[(vv * 9 + q) * 2] = w[1 + q];
+                        blk[(vv * 9 + q) * 2 + 1] = 0xffffffffu;
+                    }
+                    const uint32_t ents[4] = {w[10] & 0xffffu, w[10] >> 16, w[11] & 0xffffu, w[11] >> 16};
+                    for (uint32_t e : ents)
+                        if (e & 0x8000u) blk[(vv * 9 + ((e >> 10) & 15u)) * 2 + 1] = e & 1023u;
+                    uint32_t* hd = blk + irr_max * 18 + vv * 4;
+                    hd[0] = w[0];
+                    hd[1] = w[12];
+                    hd[2] = w[13];
+                    hd[3] = w[14];
+                }
+            int *d_home = nullptr, *d_lb = nullptr, *d_le = nullptr, *d_lc = nullptr;
+            uint32_t* d_irr = nullptr;
+            GG_TRY(dev_alloc(h, &d_home, sk.cell_home.size()));
+            GG_TRY(dev_alloc(h, &d_lb, sk.lane_begin.size()));
+            GG_TRY(dev_alloc(h, &d_le, sk.lane_end.size()));
+            GG_TRY(dev_alloc(h, &d_lc, sk.lane_cell0.size()));
+            GG_TRY(dev_alloc(h, &d_irr, blocks.size() + 16));
+            GG_CUDA_TRY(cudaMemcpy(d_home, sk.cell_home.data(), sk.cell_home.size() * sizeof(int), cudaMemcpyHostToDevice));
+            GG_CUDA_TRY(cudaMemcpy(d_lb, sk.lane_begin.data(), sk.lane_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
+            GG_CUDA_TRY(cudaMemcpy(d_le, sk.lane_end.data(), sk.lane_end.size() * sizeof(int), cudaMemcpyHostToDevice));
+            GG_CUDA_TRY(cudaMemcpy(d_lc, sk.lane_cell0.data(), sk.lane_cell0.size() * sizeof(int), cudaMemcpyHostToDevice));
+            GG_CUDA_TRY(cudaMemcpy(d_irr, blocks.data(), blocks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            float2* d_sk = nullptr;
+            float* d_sd = nullptr;
+            GG_TRY(dev_alloc(h, &d_sk, S * sk.slots));
+            GG_TRY(dev_alloc(h, &d_sd, S * sk.slots));
+            GG_CUDA_TRY(cudaMemset(d_sk, 0, S * sk.slots * sizeof(float2)));
+            GG_CUDA_TRY(cudaMemset(d_sd, 0, S * sk.slots * sizeof(float)));
+            v.skew.sk = d_sk;
+            v.skew.sd = d_sd;
+            v.skew.slots = sk.slots;
+            v.skew.cell_home = d_home;
+            v.skew.lane_begin = d_lb;
+            v.skew.lane_end = d_le;
+            v.skew.lane_cell0 = d_lc;
+            v.skew.irr_blocks = reinterpret_cast<const uint4*>(d_irr);
+            v.skew.irr_max = irr_max;
+            v.skew.irr_chunks = irr_words / 4;
+            v.skew.KP = sk.KP;
+            v.skew.rows = sk.rows;
+            v.skew.row0 = sk.row0;
+            v.skew.lanes = sk.lanes;
+            v.skew.levels = sk.levels;
+            std::memcpy(v.skew.pattern, sk.pattern, sizeof(sk.pattern));
+        }
     }
 
     if (const char* e = getenv("GG_HOST_PACK")) h->host_pack = atoi(e) ? 1 : 0;
@@ -839,7 +903,7 @@ int gg_filter_cloud_batch(gg_handle h, int count, const gg_scan_desc* scans, con
             int local = 1;
             if (const char* e = getenv("LOCAL_WORLD_SIZE")) local = std::max(1, atoi(e));
             threads = std::min(48, gg::usable_cpus() / local - 1);
-            if (threads < 6) h->host_pack = 0;
+            if (threads < 14) h->host_pack = 0;  // ~0.14 Gpts/s per packing thread vs ~1.4 Gpts/s of plain 32-byte DMA
         }
         if (h->host_pack) h->packer = new HostPacker(std::max(1, threads));
     }

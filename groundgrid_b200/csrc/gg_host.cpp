@@ -197,6 +197,215 @@ bool build_spiral_records(int n, double res_sq, const std::vector<int>& level_st
     return ok;
 }
 
+// ---- skewed-layout tables for k_spiral_skew ----------------------------------------------
+// The sweep consists of "lanes": ring k (p = c-1-k, L = 2(k+1), q = p+L) has four sides that the
+// sequential order walks cell by cell (side 0: (p, p+j), side 1: (p+j, p), side 2: (q, q-j),
+// side 3: (q-j, q)).  In the levelised schedule a lane advances one cell per level for almost all
+// of its length, and ring k+1 trails ring k by three levels.  Storing the value visited by lane
+// (s, k) at level l in slot (s, l, k) therefore makes the 3x3 neighbourhood of a visit a FIXED
+// offset pattern in (level, ring) space, and 32 consecutive rings of one side (a warp) read 32
+// consecutive slots: every load of the hot loop is coalesced.  Visits that do not follow the
+// pattern (first / last cells of a lane, ring corners with two homes) are "irregular": they carry
+// explicit slot indices and are executed by a dedicated warp.
+void build_spiral_skew(int n, const std::vector<int>& level_start, const std::vector<uint32_t>& visits, SkewTables& t) {
+    t = SkewTables();
+    t.n = n;
+    const int c = n / 2 - 1;
+    const int K = c - 1;
+    t.K = K;
+    t.levels = (int)level_start.size() - 1;
+    if (K < 2) return;
+    t.KP = ((K + 2 + 31) / 32) * 32;
+    if (4 * t.KP + 32 > 1024) return;  // one CTA: lane threads + the irregular warp
+    const size_t nv = visits.size();
+    // level of the i-th visit of every cell (level order == visit order per cell)
+    std::vector<std::vector<int>> cell_levels((size_t)n * n);
+    for (int l = 0; l < t.levels; ++l)
+        for (int v = level_start[l]; v < level_start[l + 1]; ++v) {
+            const int x = visits[v] & 0xffff, y = visits[v] >> 16;
+            cell_levels[x + (size_t)y * n].push_back(l);
+        }
+    struct Visit {
+        int s, k, j, x, y, level;
+    };
+    std::vector<Visit> seq;
+    seq.reserve(nv);
+    std::vector<int> seen((size_t)n * n, 0);
+    int max_level = 0;
+    auto push = [&](int s, int k, int j, int x, int y) {
+        const size_t cell = x + (size_t)y * n;
+        const int l = cell_levels[cell][seen[cell]++];
+        seq.push_back({s, k, j, x, y, l});
+        max_level = std::max(max_level, l);
+    };
+    for (int k = 0; k < K; ++k) {
+        const int p = c - 1 - k, L = 2 * (k + 1), q = p + L;
+        for (int j = 0; j < L; ++j) push(0, k, j, p, p + j);
+        for (int j = 0; j < L; ++j) push(1, k, j, p + j, p);
+        for (int j = 0; j <= L; ++j) push(2, k, j, q, q - j);
+        for (int j = 0; j <= L; ++j) push(3, k, j, q - j, q);
+    }
+    if (seq.size() != nv) return;
+    // start level of every lane must be 3k + off[s] (checked), used to place the never-visited cells
+    int off[4] = {0, 0, 0, 0};
+    const int k_ref = K / 2;  // the innermost rings start irregularly; take the offsets from a middle ring
+    for (const Visit& v : seq)
+        if (v.k == k_ref && v.j == 0) off[v.s] = v.level - 3 * k_ref;
+    for (const Visit& v : seq)
+        if (v.k >= 4 && v.j == 0 && v.level != 3 * v.k + off[v.s]) return;
+    const int LK = 2 * (K + 1);
+    t.rows = std::max(max_level, 3 * K + off[3] + LK + 1) + t.row0 + 8;
+    t.lanes = 4 * t.KP;
+    t.slots = (size_t)4 * t.rows * t.KP;
+    auto slot = [&](int s, int k, int level) { return (int)(((size_t)s * t.rows + level + t.row0) * t.KP + (k + 1)); };
+
+    // homes of every cell: slots of its visits; never-visited cells that are read as neighbours
+    // (centre, outermost border ring) sit where a virtual lane would visit them
+    t.cell_home.assign((size_t)n * n * 4, -1);
+    auto add_home = [&](int x, int y, int sl) {
+        int* h = &t.cell_home[((size_t)x + (size_t)y * n) * 4];
+        for (int i = 0; i < 4; ++i)
+            if (h[i] < 0) {
+                h[i] = sl;
+                return;
+            }
+    };
+    for (const Visit& v : seq) add_home(v.x, v.y, slot(v.s, v.k, v.level));
+    {
+        const int p = 0, k = K, q = p + LK;  // virtual ring K: the border the outermost ring reads
+        if (q < n) {
+            for (int j = 0; j < LK; ++j) add_home(p, p + j, slot(0, k, 3 * k + off[0] + j));
+            for (int j = 1; j < LK; ++j) add_home(p + j, p, slot(1, k, 3 * k + off[1] + j));  // (p, p) already has its side-0 home
+            for (int j = 0; j <= LK; ++j) add_home(q, q - j, slot(2, k, 3 * k + off[2] + j));
+            for (int j = 1; j <= LK; ++j)
+                if (!(q - j == p)) add_home(q - j, q, slot(3, k, 3 * k + off[3] + j));         // (p, q) keeps a single home below
+            add_home(p, q, slot(3, k, 3 * k + off[3] + LK));
+        }
+        for (int s = 0; s < 4; ++s) add_home(c, c, slot(s, -1, -3 + off[s]));  // centre: virtual ring -1
+    }
+    auto homes = [&](int x, int y) { return &t.cell_home[((size_t)x + (size_t)y * n) * 4]; };
+
+    // neighbour slot candidates + offset statistics -> the regular pattern of each side
+    std::vector<std::vector<std::pair<int, int>>> stat(36);  // (offset, count), small
+    auto bump = [&](int idx, int o) {
+        for (auto& e : stat[idx])
+            if (e.first == o) {
+                ++e.second;
+                return;
+            }
+        stat[idx].push_back({o, 1});
+    };
+    for (const Visit& v : seq) {
+        if (v.j < 3 || v.k < 4) continue;  // statistics from lane interiors only
+        const int own = slot(v.s, v.k, v.level);
+        for (int q = 0; q < 9; ++q) {
+            const int* h = homes(v.x - 1 + q % 3, v.y - 1 + q / 3);
+            for (int i = 0; i < 4 && h[i] >= 0; ++i) bump(v.s * 9 + q, h[i] - own);
+        }
+    }
+    for (int i = 0; i < 36; ++i) {
+        int best = 0, cnt = -1;
+        for (auto& e : stat[i])
+            if (e.second > cnt) {
+                cnt = e.second;
+                best = e.first;
+            }
+        if (cnt < 0) return;
+        t.pattern[i] = best;
+    }
+
+    // classify visits; irregular ones get explicit records
+    std::vector<int> last_level((size_t)n * n, -1000000), last_lane((size_t)n * n, -1);
+    t.lane_begin.assign(t.lanes, 0);
+    t.lane_end.assign(t.lanes, 0);
+    t.lane_cell0.assign(t.lanes, 0);
+    std::vector<int> reg_first(t.lanes, -1), reg_last(t.lanes, -1), reg_count(t.lanes, 0);
+    struct Irr {
+        int level;
+        uint32_t w[16];
+    };
+    std::vector<Irr> irr;
+    for (const Visit& v : seq) {
+        const int lane = v.s * t.KP + (v.k + 1);
+        const int own = slot(v.s, v.k, v.level);
+        const size_t cell = v.x + (size_t)v.y * n;
+        int nb[9];
+        bool regular = true;
+        uint32_t rec[4] = {0, 0, 0, 0};
+        int nrec = 0;
+        for (int q = 0; q < 9; ++q) {
+            const int cx = v.x - 1 + q % 3, cy = v.y - 1 + q / 3;
+            const int* h = homes(cx, cy);
+            if (h[0] < 0) return;  // a neighbour without a home: geometry not covered
+            const int want = own + t.pattern[v.s * 9 + q];
+            bool match = false;
+            for (int i = 0; i < 4 && h[i] >= 0; ++i) match |= (h[i] == want);
+            nb[q] = match ? want : h[0];
+            if (!match) regular = false;
+            const size_t ncell = cx + (size_t)cy * n;
+            const int back = v.level - last_level[ncell];
+            if (back < 1) return;  // contradicts the levelisation
+            if (back == 1) {        // written one level ago: travels through shared memory
+                if (!(q == t.prev_q[v.s] && last_lane[ncell] == lane)) regular = false;
+                if (nrec < 4) rec[nrec] = 0x8000u | ((uint32_t)q << 10) | (uint32_t)last_lane[ncell];
+                ++nrec;
+            }
+        }
+        if (nrec > 4) return;
+        if (nrec != 1) regular = false;  // a lane thread always takes its previous cell from the exchange buffer
+        const int* hown = homes(v.x, v.y);
+        int mirror = -1;
+        if (hown[1] >= 0) {
+            regular = false;  // a ring corner: both homes are kept identical
+            mirror = (hown[0] == own) ? hown[1] : hown[0];
+            if (hown[2] >= 0) return;
+        }
+        if (regular) {
+            ++t.n_regular;
+            if (reg_first[lane] < 0) {
+                reg_first[lane] = v.level;
+                t.lane_cell0[lane] = (int)cell;
+            }
+            if (reg_last[lane] >= 0 && v.level != reg_last[lane] + 1) return;  // the regular run must be contiguous in levels
+            reg_last[lane] = v.level;
+            ++reg_count[lane];
+        } else {
+            ++t.n_irregular;
+            Irr r;
+            r.level = v.level;
+            std::memset(r.w, 0, sizeof(r.w));
+            r.w[0] = (uint32_t)own;
+            for (int q = 0; q < 9; ++q) r.w[1 + q] = (uint32_t)nb[q];
+            r.w[10] = rec[0] | (rec[1] << 16);
+            r.w[11] = rec[2] | (rec[3] << 16);
+            r.w[12] = (uint32_t)mirror;
+            r.w[13] = (uint32_t)lane;
+            r.w[14] = (uint32_t)cell;
+            irr.push_back(r);
+        }
+        last_level[cell] = v.level;
+        last_lane[cell] = lane;
+    }
+    for (int l = 0; l < t.lanes; ++l)
+        if (reg_first[l] >= 0) {
+            t.lane_begin[l] = reg_first[l];
+            t.lane_end[l] = reg_last[l] + 1;
+            if (t.lane_end[l] - t.lane_begin[l] != reg_count[l]) return;
+        }
+    // CSR of the irregular visits by level
+    t.irr_level_start.assign((size_t)t.levels + 1, 0);
+    for (const Irr& r : irr) ++t.irr_level_start[(size_t)r.level + 1];
+    for (int l = 0; l < t.levels; ++l) {
+        t.max_irr_per_level = std::max(t.max_irr_per_level, t.irr_level_start[(size_t)l + 1]);
+        t.irr_level_start[(size_t)l + 1] += t.irr_level_start[l];
+    }
+    if (t.max_irr_per_level > 32) return;
+    t.irr_recs.assign(irr.size() * 16, 0u);
+    std::vector<int> cur(t.irr_level_start.begin(), t.irr_level_start.end() - 1);
+    for (const Irr& r : irr) std::memcpy(&t.irr_recs[(size_t)cur[r.level]++ * 16], r.w, sizeof(r.w));
+    t.ok = true;
+}
+
 // ---- host-side cloud packing (gg_filter_cloud_batch) -------------------------------------
 // PointXYZIR records (32 B, 14 useful) -> x | y | z (float[n_pad]) | ring (u16[n_pad]) with
 // n_pad = n rounded up to 8, written with streaming stores into pinned staging memory.
@@ -339,6 +548,26 @@ int gg_host_spiral_records(int n, float resolution, int dist, uint32_t* recs, in
     if (max_recent) *max_recent = mr;
     if (recs && rec_cap_words >= (int)rc.size()) std::memcpy(recs, rc.data(), rc.size() * sizeof(uint32_t));
     return ok ? 1 : 0;
+}
+
+// header: ok, K, KP, rows, levels, row0, lanes, n_irregular, max_irr_per_level, n_regular
+int gg_host_spiral_skew(int n, int* header, int* pattern, int* lane_begin, int* lane_end, int* cell_home, int* irr_level_start,
+                        uint32_t* irr_recs, int irr_cap_words) {
+    std::vector<int> ls;
+    std::vector<uint32_t> vs;
+    gg::build_spiral_schedule(n, ls, vs);
+    gg::SkewTables t;
+    gg::build_spiral_skew(n, ls, vs, t);
+    const int h[10] = {t.ok ? 1 : 0, t.K, t.KP, t.rows, t.levels, t.row0, t.lanes, (int)t.n_irregular, t.max_irr_per_level, (int)t.n_regular};
+    std::memcpy(header, h, sizeof(h));
+    if (!t.ok) return 0;
+    if (pattern) std::memcpy(pattern, t.pattern, sizeof(t.pattern));
+    if (lane_begin) std::memcpy(lane_begin, t.lane_begin.data(), t.lane_begin.size() * sizeof(int));
+    if (lane_end) std::memcpy(lane_end, t.lane_end.data(), t.lane_end.size() * sizeof(int));
+    if (cell_home) std::memcpy(cell_home, t.cell_home.data(), t.cell_home.size() * sizeof(int));
+    if (irr_level_start) std::memcpy(irr_level_start, t.irr_level_start.data(), t.irr_level_start.size() * sizeof(int));
+    if (irr_recs && irr_cap_words >= (int)t.irr_recs.size()) std::memcpy(irr_recs, t.irr_recs.data(), t.irr_recs.size() * sizeof(uint32_t));
+    return 1;
 }
 
 int gg_host_move_map(double res, double* pos_xy, double nx, double ny, int* shift_ij) {

@@ -13,6 +13,24 @@ void move_map(double res, double& px, double& py, double nx, double ny, int& shi
 void build_spiral_schedule(int n, std::vector<int>& level_start, std::vector<uint32_t>& visits);
 void pack_cloud_range(const gg_point* src, size_t n, unsigned char* dst, size_t i0, size_t i1);
 int usable_cpus();
+
+// Tables of the skewed-layout spiral kernel (k_spiral_skew), see gg_host.cpp:build_spiral_skew.
+struct SkewTables {
+    bool ok = false;
+    int n = 0, K = 0, KP = 0, rows = 0, levels = 0, row0 = 8;
+    int lanes = 0;                       // 4 * KP
+    size_t slots = 0;                    // 4 * rows * KP
+    int pattern[36] = {0};               // [side][q]: slot offset of neighbour q relative to the own slot (regular visits)
+    int prev_q[4] = {1, 3, 7, 5};        // neighbour index of a lane's previous cell
+    std::vector<int> lane_begin, lane_end;   // [lanes] level range [begin, end) of the lane's regular run
+    std::vector<int> lane_cell0;             // [lanes] cell (x + y * n) of the first regular visit; the lane then steps by +n, +1, -n, -1 (side 0..3)
+    std::vector<int> cell_home;          // [n * n * 4] slots holding a copy of the cell (-1 padded; [0] first visit, [1] second visit)
+    std::vector<int> irr_level_start;    // [levels + 1] CSR over levels
+    std::vector<uint32_t> irr_recs;      // 16 words per irregular visit: own, nb[9], recents01, recents23, mirror, lane, cell, pad
+    int max_irr_per_level = 0;
+    size_t n_regular = 0, n_irregular = 0;
+};
+void build_spiral_skew(int n, const std::vector<int>& level_start, const std::vector<uint32_t>& visits, SkewTables& t);
 bool build_spiral_records(int n, double res_sq, const std::vector<int>& level_start, const std::vector<uint32_t>& visits,
                           int dist, std::vector<uint32_t>& recs, int& max_recent);
 }  // namespace gg
@@ -25,4 +43,5 @@ int gg_host_spiral_schedule(int n, int* level_start, int level_cap, uint32_t* vi
 int gg_host_spiral_records(int n, float resolution, int dist, uint32_t* recs, int rec_cap_words, int* max_recent);
 int gg_host_move_map(double res, double* pos_xy, double nx, double ny, int* shift_ij);
 int gg_host_pack_cloud(const gg_point* src, size_t n, unsigned char* dst);
+int gg_host_spiral_skew(int n, int* header, int* pattern, int* lane_begin, int* lane_end, int* cell_home, int* irr_level_start, uint32_t* irr_recs, int irr_cap_words);
 }

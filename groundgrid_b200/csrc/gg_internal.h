@@ -71,6 +71,25 @@ struct SlotParams {
     const float* packed;
 };
 
+// Device side of the skewed-layout spiral (gg_host.h:SkewTables); null sk -> not used.
+struct SkewView {
+    float2* sk;             // [n_slots][slots] (G, C) in (side, level, ring) order
+    float* sd;              // [n_slots][slots] decayed confidence the visit will store, -1: confidence unchanged
+    size_t slots;
+    const int* cell_home;   // [N2][4]
+    const int* lane_begin;  // [lanes]
+    const int* lane_end;
+    const int* lane_cell0;  // [lanes] cell of the lane's first regular visit
+    // irregular visits, one fixed-size block per level (irr_chunks x uint4):
+    //   words [ (v * 9 + q) * 2 + {0, 1} ] = slot of neighbour q of visit v, producer lane if it was
+    //                                        written one level ago (else 0xffffffff)
+    //   words [ irr_max * 18 + v * 4 + {0..3} ] = own slot (0xffffffff: no visit), mirror slot, lane, cell
+    const uint4* irr_blocks;
+    int irr_max, irr_chunks;
+    int KP, rows, row0, lanes, levels;
+    int pattern[36];
+};
+
 // Pointers / strides of the handle's device arena, passed to kernels by value.
 struct View {
     Const k;
@@ -107,6 +126,7 @@ struct View {
     const uint4* spiral_recs; // null -> plain k_spiral
     int spiral_dist;          // prefetch distance the records were built for (1..3)
     int spiral_threads;       // 512 or 1024 (>= max visits per level)
+    SkewView skew;            // skew.sk != null -> k_skew + k_spiral_skew + k_unskew replace k_spiral_pipe
 
     __host__ __device__ float* layer(int slot, int l) const { return layers + ((size_t)slot * n_layers + l) * k.N2; }
 };

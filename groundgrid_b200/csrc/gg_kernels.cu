@@ -456,6 +456,33 @@ __device__ __forceinline__ float decay_confidence(const Const& k, float occ) {
     return (float)((dec < 0.001) ? 0.001 : dec);
 }
 
+// Fused into k_detect: every cell is copied to its home slot(s) as soon as its final G, C are known.
+__device__ __forceinline__ void skew_store_cell(const View& v, const SlotParams& sp, int cell, int x, int y, float g, float c) {
+    const Const& k = v.k;
+    const int4 home = __ldg(reinterpret_cast<const int4*>(v.skew.cell_home) + cell);
+    if (home.x < 0) return;
+    const int cidx = k.N / 2 - 1;
+    if (x == cidx && y == cidx) {  // spiral_ground_interpolation :405,411 (the normal layers get it in k_spiral_skew)
+        g = sp.base_z_f;
+        c = 1.0f;
+    }
+    // :463: beyond minDistSquared the visit stores the decayed confidence (:464)
+    const float fx = __fsub_rn((float)x, (float)cidx), fy = __fsub_rn((float)y, (float)cidx);
+    const bool far = __dmul_rn(__dadd_rn(__dmul_rn((double)fx, (double)fx), __dmul_rn((double)fy, (double)fy)), k.res_sq) > 12.0;
+    const float d1 = far ? decay_confidence(k, c) : -1.0f;
+    float2* SK = v.skew.sk + (size_t)sp.slot * v.skew.slots;
+    float* SD = v.skew.sd + (size_t)sp.slot * v.skew.slots;
+    const float2 gc = make_float2(g, c);
+    SK[home.x] = gc;
+    SD[home.x] = d1;
+    if (home.y >= 0) {
+        SK[home.y] = gc;
+        SD[home.y] = far ? decay_confidence(k, d1) : -1.0f;  // second visit of a ring corner
+    }
+    if (home.z >= 0) SK[home.z] = gc;
+    if (home.w >= 0) SK[home.w] = gc;
+}
+
 template <int S>
 __device__ __forceinline__ void detect_patch(const Const& k, const float (*sP)[DT_W], const float (*sV)[DT_W], const float (*sM)[DT_W],
                                              int li, int lj, float sqdist, float e, float* Gp, float* Cp) {
@@ -541,7 +568,9 @@ __global__ void __launch_bounds__(DT_X* DT_Y) k_detect(View v, const SlotParams*
         else
             detect_patch<5>(k, sP, sV, sM, li, lj, sqdist, e, Gp, Cp);
     }
-    if (v.spiral_recs) {
+    if (v.skew.sk) {
+        skew_store_cell(v, sp, i + j * N, i, j, *Gp, *Cp);
+    } else if (v.spiral_recs) {
         // Decayed confidence for the spiral sweep, taken off its sequential critical path: the
         // confidence of a cell only changes at its own visit(s), so decay(C) after patch
         // detection is exactly what the (first) visit will store; ring corners (i == j) are
@@ -750,6 +779,245 @@ __global__ void __launch_bounds__(THREADS) k_spiral_pipe(View v, const SlotParam
 }
 
 // ------------------------------------------------------------------------------------------
+// Skewed-layout spiral.  k_detect copies G, C (and the confidence each visit will store) into
+// (side, level, ring) order (skew_store_cell), k_spiral_skew runs the wavefront there with
+// coalesced accesses and also stores every result to the normal layers.  See
+// gg_host.cpp:build_spiral_skew for the layout.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 spiral_visit(const float2* nb, float d) {
+    float cc[9], pr[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        cc[q] = nb[q].y;
+        pr[q] = __fmul_rn(nb[q].y, nb[q].x);
+    }
+    const float occ = cc[4], h = nb[4].x;
+    const float ssum = __fadd_rn(tree9(cc), FLT_MIN);  // :457
+    const float avg = __fdiv_rn(tree9(pr), ssum);      // :458
+    const float newg = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, occ), avg), __fmul_rn(occ, h));  // :460
+    return make_float2(newg, d >= 0.0f ? d : occ);     // :463-464 via the table of k_skew
+}
+
+// The level time of this kernel is set by the longest per-warp INSTRUCTION sequence between two
+// barriers (one SM, a handful of active warps: a warp issues its dependent instructions a few
+// cycles apart), not by memory.  So both roles keep their per-level code short: lane threads are
+// compiled per side (compile-time neighbour index of the lane's previous cell, running pointers),
+// and the irregular visits are spread over 64 threads (one thread per (visit, neighbour) gathers,
+// one thread per visit computes) instead of unrolled in one thread.
+constexpr int SKEW_IRR_THREADS = 64;
+constexpr int SKEW_RING = 16;      // levels of irregular-visit blocks kept in shared memory
+constexpr int SKEW_STAGE_LEAD = 10;  // a block is staged this many levels before its visits run
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+template <int SIDE>
+__device__ __forceinline__ void skew_lane_thread(const View& v, const SlotParams& sp, float2* s_xch) {
+    const SkewView& w = v.skew;
+    constexpr int PQ = SIDE == 0 ? 1 : (SIDE == 1 ? 3 : (SIDE == 2 ? 7 : 5));  // neighbour index of the lane's previous cell
+    const int tid = threadIdx.x;
+    const int L = w.levels, KP = w.KP, lanes = w.lanes;
+    float2* __restrict__ SK = w.sk + (size_t)sp.slot * w.slots;
+    const float* __restrict__ SD = w.sd + (size_t)sp.slot * w.slots;
+    const int lb = w.lane_begin[tid], le = w.lane_end[tid];
+    float* __restrict__ Gn = v.layer(sp.slot, L_GROUND);
+    float* __restrict__ Cn = v.layer(sp.slot, L_GROUNDPATCH);
+    const int cstep = SIDE == 0 ? v.k.N : (SIDE == 1 ? 1 : (SIDE == 2 ? -v.k.N : -1));  // the lane walks +y, +x, -y, -x
+    const int cell0 = w.lane_cell0[tid] - lb * cstep;                                      // cell of level l: cell0 + l * cstep
+    int off[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) off[q] = w.pattern[SIDE * 9 + q];
+    // slot of this lane at level l: base0 + l * KP
+    const int base0 = (SIDE * w.rows + w.row0) * KP + (tid - SIDE * KP);
+    float2 A[9], B[9];
+    float dA = -1.0f, dB = -1.0f;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) A[q] = B[q] = make_float2(0.f, 0.f);
+    if (lb == 0 && le > 0) {
+#pragma unroll
+        for (int q = 0; q < 9; ++q) A[q] = SK[base0 + off[q]];
+        dA = SD[base0];
+    }
+    // The only slot a regular visit touches for the first time (i.e. that still sits in HBM / L2) is
+    // the newest row of its outer ring, plus its SD entry; everything else was read by this SM a
+    // few levels ago.  Those two are prefetched PF_FAR levels ahead into L2 and PF_NEAR levels ahead
+    // into L1, so the one-level-ahead loads below are cache hits.
+    int off_new = off[0];
+#pragma unroll
+    for (int q = 1; q < 9; ++q) off_new = max(off_new, off[q]);
+    constexpr int PF_FAR = 8, PF_NEAR = 2;
+    // two levels per iteration, alternating register sets (a copy would wait for the loads)
+#define GG_LANE_LEVEL(l_, CUR, CURD, NXT, NXTD)                                                      \
+    {                                                                                               \
+        const int l__ = (l_);                                                                       \
+        if (l__ + PF_FAR >= lb && l__ + PF_FAR < le) {                                              \
+            prefetch_l2(SK + (base0 + (l__ + PF_FAR) * KP + off_new));                              \
+            prefetch_l2(SD + (base0 + (l__ + PF_FAR) * KP));                                        \
+        }                                                                                           \
+        if (l__ + PF_NEAR >= lb && l__ + PF_NEAR < le) {                                            \
+            prefetch_l1(SK + (base0 + (l__ + PF_NEAR) * KP + off_new));                             \
+            prefetch_l1(SD + (base0 + (l__ + PF_NEAR) * KP));                                       \
+        }                                                                                           \
+        if (l__ + 1 >= lb && l__ + 1 < le) {                                                        \
+            const float2* p__ = SK + (base0 + (l__ + 1) * KP);                                      \
+            _Pragma("unroll") for (int q = 0; q < 9; ++q) NXT[q] = p__[off[q]];                    \
+            NXTD = SD[base0 + (l__ + 1) * KP];                                                      \
+        }                                                                                           \
+        if (l__ >= lb && l__ < le) {                                                                \
+            CUR[PQ] = s_xch[((l__ + 1) & 1) * lanes + tid];                                         \
+            const float2 r__ = spiral_visit(CUR, CURD);                                             \
+            s_xch[(l__ & 1) * lanes + tid] = r__;                                                   \
+            SK[base0 + l__ * KP] = r__;                                                             \
+            Gn[cell0 + l__ * cstep] = r__.x;                                                        \
+            if (CURD >= 0.0f) Cn[cell0 + l__ * cstep] = r__.y;                                      \
+        }                                                                                           \
+        __syncthreads();                                                                            \
+    }
+    // a warp (32 consecutive rings of one side) has work only in a window of levels; outside of it
+    // the per-level cost must be the barrier alone (the level time is set by instruction issue)
+    int w_first = lb < le ? lb - PF_FAR : 0x7fffffff, w_last = lb < le ? le : -1;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        w_first = min(w_first, __shfl_xor_sync(0xffffffffu, w_first, d));
+        w_last = max(w_last, __shfl_xor_sync(0xffffffffu, w_last, d));
+    }
+    w_first = max(w_first, 0) & ~1;  // iterations cover two levels
+    for (int l = 0; l < L; l += 2) {
+        if (l < w_first || l >= w_last) {
+            __syncthreads();
+            if (l + 1 < L) __syncthreads();
+            continue;
+        }
+        GG_LANE_LEVEL(l, A, dA, B, dB)
+        if (l + 1 < L) GG_LANE_LEVEL(l + 1, B, dB, A, dA)
+    }
+#undef GG_LANE_LEVEL
+}
+
+__device__ __forceinline__ void skew_named_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(SKEW_IRR_THREADS) : "memory"); }
+
+__device__ __forceinline__ void skew_irregular_thread(const View& v, const SlotParams& sp, float2* s_xch, uint4* s_ring, float2* s_nb, float* s_dd) {
+    const SkewView& w = v.skew;
+    const int ti = threadIdx.x - w.lanes;  // 0 .. 63
+    const int L = w.levels, lanes = w.lanes;
+    const int chunks = w.irr_chunks, irr_max = w.irr_max;
+    float2* __restrict__ SK = w.sk + (size_t)sp.slot * w.slots;
+    const float* __restrict__ SD = w.sd + (size_t)sp.slot * w.slots;
+    const uint4* __restrict__ blocks = w.irr_blocks;
+    float* __restrict__ Gn = v.layer(sp.slot, L_GROUND);
+    float* __restrict__ Cn = v.layer(sp.slot, L_GROUNDPATCH);
+    if (ti == 0) {  // spiral_ground_interpolation :405,411 on the normal layers (the skewed copy has it from k_detect)
+        const int cidx = v.k.N / 2 - 1;
+        Cn[cidx + cidx * v.k.N] = 1.0f;
+        Gn[cidx + cidx * v.k.N] = sp.base_z_f;
+    }
+    const uint32_t* ring_w = reinterpret_cast<const uint32_t*>(s_ring);
+    const int ring_words = chunks * 4;
+    const bool stager = ti < chunks;              // copies one 16-byte chunk of the level blocks per level
+    const bool gatherer = ti < irr_max * 9;       // (visit ti / 9, neighbour ti % 9)
+    const bool visitor = ti < irr_max;            // computes visit ti
+
+    // prologue: blocks of levels 0 .. LEAD-1 -> ring; gather of level 0; block of level LEAD in flight
+    if (stager) {
+        for (int b = 0; b < SKEW_STAGE_LEAD; ++b) s_ring[b * chunks + ti] = blocks[(size_t)min(b, L + 3) * chunks + ti];  // the table has 4 padding levels
+    }
+    uint4 stage = stager ? blocks[(size_t)min(SKEW_STAGE_LEAD, L + 3) * chunks + ti] : make_uint4(0, 0, 0, 0);
+    skew_named_barrier();
+    float2 val = make_float2(0.f, 0.f);
+    float dval = -1.0f;
+    uint32_t info = 0xffffffffu;
+    bool have = false;
+    if (gatherer) {
+        const uint32_t slot = ring_w[0 * ring_words + ti * 2], rl = ring_w[0 * ring_words + ti * 2 + 1];
+        have = slot != 0xffffffffu;
+        if (have) {
+            val = SK[slot];
+            info = rl;
+            if (ti % 9 == 4) dval = SD[slot];
+        }
+    }
+    for (int l = 0; l < L; ++l) {
+        // (1) block of level l + LEAD (loaded during the previous level) -> ring; start loading the next one
+        if (stager) {
+            s_ring[((l + SKEW_STAGE_LEAD) % SKEW_RING) * chunks + ti] = stage;
+            stage = blocks[(size_t)min(l + SKEW_STAGE_LEAD + 1, L + 3) * chunks + ti];
+        }
+        // (2) hand the gathered neighbour of THIS level to the visitor, gather the one of level l + 1,
+        //     pull the one of level l + LEAD - 2 towards L2 / L1
+        if (gatherer) {
+            if (have) {
+                if (info != 0xffffffffu) val = s_xch[((l + 1) & 1) * lanes + (int)info];  // written at level l - 1
+                s_nb[ti] = val;
+                if (ti % 9 == 4) s_dd[ti / 9] = dval;
+            }
+            const uint32_t far_slot = ring_w[((l + SKEW_STAGE_LEAD - 2) % SKEW_RING) * ring_words + ti * 2];
+            if (far_slot != 0xffffffffu) {
+                prefetch_l2(SK + far_slot);
+                if (ti % 9 == 4) prefetch_l2(SD + far_slot);
+            }
+            const uint32_t near_slot = ring_w[((l + 3) % SKEW_RING) * ring_words + ti * 2];
+            if (near_slot != 0xffffffffu) {
+                prefetch_l1(SK + near_slot);
+                if (ti % 9 == 4) prefetch_l1(SD + near_slot);
+            }
+            const uint32_t* e = ring_w + ((l + 1) % SKEW_RING) * ring_words + ti * 2;
+            const uint32_t slot = e[0];
+            have = (l + 1 < L) && slot != 0xffffffffu;
+            if (have) {
+                val = SK[slot];
+                info = e[1];
+                if (ti % 9 == 4) dval = SD[slot];
+            }
+        }
+        skew_named_barrier();
+        // (3) the visits of this level
+        if (visitor) {
+            const uint32_t* hd = ring_w + (l % SKEW_RING) * ring_words + irr_max * 18 + ti * 4;
+            const uint32_t own = hd[0];
+            if (own != 0xffffffffu) {
+                float2 nb[9];
+#pragma unroll
+                for (int q = 0; q < 9; ++q) nb[q] = s_nb[ti * 9 + q];
+                const float2 r = spiral_visit(nb, s_dd[ti]);
+                const int mirror = (int)hd[1];
+                s_xch[(l & 1) * lanes + (int)hd[2]] = r;
+                SK[own] = r;
+                if (mirror >= 0) SK[mirror] = r;
+                Gn[hd[3]] = r.x;
+                if (s_dd[ti] >= 0.0f) Cn[hd[3]] = r.y;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) k_spiral_skew(View v, const SlotParams* __restrict__ batch) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const SkewView& w = v.skew;
+    // [ring: SKEW_RING levels x irr_chunks uint4][xch: 2 x lanes float2][nb: irr_max*9 float2][dd: irr_max float]
+    uint4* s_ring = reinterpret_cast<uint4*>(s_raw);
+    float2* s_xch = reinterpret_cast<float2*>(s_ring + SKEW_RING * w.irr_chunks);
+    float2* s_nb = s_xch + 2 * w.lanes;
+    float* s_dd = reinterpret_cast<float*>(s_nb + w.irr_max * 9);
+    const SlotParams& sp = batch[blockIdx.x];
+    const int tid = threadIdx.x;
+    if (tid < w.lanes) {
+        const int side = tid / w.KP;  // warp-uniform: KP is a multiple of 32
+        if (side == 0)
+            skew_lane_thread<0>(v, sp, s_xch);
+        else if (side == 1)
+            skew_lane_thread<1>(v, sp, s_xch);
+        else if (side == 2)
+            skew_lane_thread<2>(v, sp, s_xch);
+        else
+            skew_lane_thread<3>(v, sp, s_xch);
+    } else {
+        skew_irregular_thread(v, sp, s_xch, s_ring, s_nb, s_dd);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // phase 4: labelling (:146-196)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_label(View v, const SlotParams* __restrict__ batch) {
@@ -934,7 +1202,15 @@ int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int 
     ++launches;
     if (stop_after == 2) return launches;
 
-    if (v.spiral_recs) {
+    if (v.skew.sk) {
+        const int threads = v.skew.lanes + SKEW_IRR_THREADS;
+        const size_t shm = (size_t)SKEW_RING * v.skew.irr_chunks * sizeof(uint4) + (size_t)2 * v.skew.lanes * sizeof(float2) +
+                           (size_t)v.skew.irr_max * 9 * sizeof(float2) + (size_t)v.skew.irr_max * sizeof(float) + 16;
+        if (threads <= 768)
+            GG_LAUNCH(K_SPIRAL, k_spiral_skew<768><<<count, threads, shm, st>>>(v, batch));
+        else
+            GG_LAUNCH(K_SPIRAL, k_spiral_skew<1024><<<count, threads, shm, st>>>(v, batch));
+    } else if (v.spiral_recs) {
         const size_t shm = (size_t)((v.levels + 4) & ~3) * sizeof(int) + (size_t)(v.spiral_dist + 1) * v.spiral_threads * sizeof(float2);
 #define GG_SPIRAL_CASE(T, D)                                                                      \
     if (v.spiral_threads == T && v.spiral_dist == D) {                                            \

@@ -261,3 +261,135 @@ def test_host_cloud_packing(n):
     assert np.array_equal(dst[12 * n_pad:].view(np.uint16)[:n], pts["ring"])
     assert np.all(f[n:n_pad] == 0) and np.all(dst[12 * n_pad:].view(np.uint16)[n:] == 0)
     assert np.all(raw[off + 14 * n_pad:] == 0xAB)
+
+
+def host_spiral_skew(n):
+    import ctypes as C
+
+    L = capi.load()
+    fn = L.gg_host_spiral_skew
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int] + [C.c_void_p] * 7 + [C.c_int]
+    hdr = np.zeros(10, np.int32)
+    fn(n, hdr.ctypes.data, None, None, None, None, None, None, 0)
+    if not hdr[0]:
+        return None
+    K, KP, rows, levels, row0, lanes, n_irr = (int(v) for v in hdr[1:8])
+    pattern = np.zeros(36, np.int32)
+    lb, le = np.zeros(lanes, np.int32), np.zeros(lanes, np.int32)
+    home = np.zeros(n * n * 4, np.int32)
+    ils = np.zeros(levels + 1, np.int32)
+    recs = np.zeros(n_irr * 16, np.uint32)
+    assert fn(n, hdr.ctypes.data, pattern.ctypes.data, lb.ctypes.data, le.ctypes.data, home.ctypes.data, ils.ctypes.data, recs.ctypes.data, recs.size) == 1
+    return dict(K=K, KP=KP, rows=rows, levels=levels, row0=row0, lanes=lanes, pattern=pattern.reshape(4, 9), lane_begin=lb, lane_end=le,
+                home=home.reshape(n * n, 4), irr_level_start=ils, irr=recs.reshape(-1, 16))
+
+
+@pytest.mark.parametrize("dim,res", [(13.2, 0.33), (33.0, 0.33), (99.0, 0.33), (120.0, 0.33)])
+def test_skewed_spiral_tables_emulation(dim, res):
+    """CPU emulation of k_skew -> k_spiral_skew -> k_unskew: lane threads follow the fixed offset
+    pattern in (level, ring) space, the irregular warp follows explicit records, neighbourhoods are
+    read one level ahead, values written one level ago arrive through the per-lane exchange buffer.
+    Must equal the oracle's sequential sweep bit for bit."""
+    o = Oracle(dim, res)
+    n = o.n
+    t = host_spiral_skew(n)
+    assert t is not None
+    KP, rows, row0, lanes, L = t["KP"], t["rows"], t["row0"], t["lanes"], t["levels"]
+    prev_q = [1, 3, 7, 5]
+    rng = np.random.default_rng(17)
+    o.init_map(0.0, 0.0, 0.0)
+    G = rng.uniform(-1, 1, (n, n)).astype(np.float32)
+    C = (rng.uniform(0, 1, (n, n)) ** 4).astype(np.float32)
+    o.set_layer("ground", G)
+    o.set_layer("groundpatch", C)
+    o.spiral(0.3)
+
+    # ---- k_skew (column-major cell index = i + j * n)
+    c = n // 2 - 1
+    Gf, Cf = G.reshape(-1, order="F").copy(), C.reshape(-1, order="F").copy()
+    Gf[c + c * n] = f32(0.3)
+    Cf[c + c * n] = 1.0
+    o64 = Cf.astype(np.float64)
+    D1 = np.maximum(o64 - o64 / 5.0, 0.001).astype(np.float32)
+    d64 = D1.astype(np.float64)
+    D2 = np.maximum(d64 - d64 / 5.0, 0.001).astype(np.float32)
+    ii, jj = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    fx = (ii.astype(np.float32) - f32(c)).astype(np.float64)
+    fy = (jj.astype(np.float32) - f32(c)).astype(np.float64)
+    far = ((fx * fx + fy * fy) * np.float64(f32(res)) ** 2 > 12.0).reshape(-1, order="F")
+    nslots = 4 * rows * KP
+    SKg, SKc, SD = np.zeros(nslots, np.float32), np.zeros(nslots, np.float32), np.full(nslots, -1.0, np.float32)
+    home = t["home"]
+    for h in range(4):
+        m = home[:, h] >= 0
+        SKg[home[m, h]] = Gf[m]
+        SKc[home[m, h]] = Cf[m]
+        if h < 2:
+            SD[home[m, h]] = np.where(far[m], (D1 if h == 0 else D2)[m], f32(-1.0))
+    # ---- k_spiral_skew
+    lane = np.arange(lanes)
+    side, kcol = lane // KP, lane % KP
+    xg, xc = np.zeros((2, lanes), np.float32), np.zeros((2, lanes), np.float32)
+    irr, ils = t["irr"], t["irr_level_start"]
+
+    def reg_lanes(lvl):
+        return lane[(t["lane_begin"] <= lvl) & (lvl < t["lane_end"])]
+
+    def fetch(lvl):  # what the prefetch of level `lvl` sees
+        rl = reg_lanes(lvl)
+        own = (side[rl] * rows + lvl + row0) * KP + kcol[rl]
+        idx = own[:, None] + t["pattern"][side[rl]]
+        r = irr[ils[lvl]:ils[lvl + 1]]
+        iidx = r[:, 1:10].astype(np.int64)
+        return (rl, own, SKg[idx].copy(), SKc[idx].copy(), SD[own].copy(), r, SKg[iidx].copy(), SKc[iidx].copy(), SD[r[:, 0].astype(np.int64)].copy())
+
+    def tree(v):
+        return ((v[:, 0] + v[:, 1]) + (v[:, 2] + v[:, 3])) + ((v[:, 4] + v[:, 5]) + (v[:, 6] + (v[:, 7] + v[:, 8])))
+
+    def visit(gg, cc, dd):
+        s = tree(cc) + FLT_MIN
+        avg = tree(cc * gg) / s
+        occ = cc[:, 4]
+        newg = (f32(1.0) - occ) * avg + occ * gg[:, 4]
+        newc = np.where(dd >= 0, dd, occ).astype(np.float32)
+        return newg.astype(np.float32), newc
+
+    nxt = fetch(0)
+    for lvl in range(L):
+        cur = nxt
+        if lvl + 1 < L:
+            nxt = fetch(lvl + 1)       # issued before this level's stores
+        rl, own, gg, cc, dd, r, igg, icc, idd = cur
+        pb = (lvl - 1) & 1
+        # regular lanes: the previous cell of the lane comes from the exchange buffer
+        if len(rl) and lvl > 0:
+            pq = np.array(prev_q)[side[rl]]
+            gg[np.arange(len(rl)), pq] = xg[pb, rl]
+            cc[np.arange(len(rl)), pq] = xc[pb, rl]
+        ng, nc = visit(gg, cc, dd)
+        # irregular visits: recents name (neighbour, producer lane)
+        for w in (10, 11):
+            for sh in (0, 16):
+                e = (r[:, w] >> sh) & 0xFFFF
+                m = (e & 0x8000) != 0
+                q = ((e >> 10) & 15).astype(np.int64)
+                pl = (e & 1023).astype(np.int64)
+                igg[m, q[m]] = xg[pb, pl[m]]
+                icc[m, q[m]] = xc[pb, pl[m]]
+        ing, inc = visit(igg, icc, idd)
+        # stores
+        SKg[own], SKc[own] = ng, nc
+        xg[lvl & 1, rl], xc[lvl & 1, rl] = ng, nc
+        io = r[:, 0].astype(np.int64)
+        SKg[io], SKc[io] = ing, inc
+        mir = r[:, 12].astype(np.int32)
+        mm = mir >= 0
+        SKg[mir[mm]], SKc[mir[mm]] = ing[mm], inc[mm]
+        il = r[:, 13].astype(np.int64)
+        xg[lvl & 1, il], xc[lvl & 1, il] = ing, inc
+    # ---- k_unskew
+    m = home[:, 0] >= 0
+    Gf[m], Cf[m] = SKg[home[m, 0]], SKc[home[m, 0]]
+    assert np.array_equal(o.layer("ground"), Gf.reshape(n, n, order="F"))
+    assert np.array_equal(o.layer("groundpatch"), Cf.reshape(n, n, order="F"))
