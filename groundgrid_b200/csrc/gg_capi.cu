@@ -508,11 +508,15 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
     GG_TRY(dev_alloc(h, &v.raw_i, (flags & GG_FLAG_FULL_LAYERS) ? S * N2 : 1));
     GG_TRY(dev_alloc(h, &v.cellstart, S * N2));
     GG_TRY(dev_alloc(h, &v.sort_hist, S * ((size_t)v.sort_blocks << bits_max)));
+    GG_TRY(dev_alloc(h, &v.sort_hist2, S * ((size_t)v.sort_blocks << bits_max)));
     GG_TRY(dev_alloc(h, &v.out_index, S * P));
     GG_TRY(dev_alloc(h, &v.out_counts, S * (3 * (size_t)v.out_blocks + 1)));
     GG_TRY(dev_alloc(h, &v.roll_scratch, S * 2 * N2));
     v.out_cloud = nullptr;
     GG_CUDA_TRY(cudaMemset(v.layers, 0, S * v.n_layers * N2 * sizeof(float)));
+    // per-cell counters are zero between scans (k_cell_stats resets what it consumed)
+    GG_CUDA_TRY(cudaMemset(v.cnt_i, 0, S * N2 * sizeof(int)));
+    if (flags & GG_FLAG_FULL_LAYERS) GG_CUDA_TRY(cudaMemset(v.raw_i, 0, S * N2 * sizeof(int)));
 
     // expectedPoints table (host libm, like the reference) and the spiral wavefront schedule
     {
@@ -820,10 +824,9 @@ int gg_profile_read(gg_handle h, double* ms_per_kernel, uint32_t* launches_per_k
 int gg_profile_kernel_count(void) { return gg::K_NUM; }
 
 const char* gg_profile_kernel_name(int id) {
-    static const char* names[gg::K_NUM] = {"k_clear_scan",  "k_rasterize",     "k_sort_hist(lo)", "k_sort_scan(lo)", "k_sort_scatter(lo)",
-                                           "k_sort_hist(hi)", "k_sort_scan(hi)", "k_sort_scatter(hi)", "k_scan_cells", "k_cell_stats",
-                                           "k_detect",      "k_spiral",        "k_label",         "k_roll_gather",   "k_roll_commit",
-                                           "k_out_count",   "k_out_scan",      "k_out_write"};
+    static const char* names[gg::K_NUM] = {"k_rasterize",   "k_scan_lo_cells", "k_sort_scatter(lo)", "k_sort_scan(hi)", "k_sort_scatter(hi)",
+                                           "k_cell_stats",  "k_detect",        "k_spiral",           "k_label",         "k_roll_gather",
+                                           "k_roll_commit", "k_out_count",     "k_out_scan",         "k_out_write"};
     return (id >= 0 && id < gg::K_NUM) ? names[id] : "";
 }
 

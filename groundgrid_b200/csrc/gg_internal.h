@@ -109,7 +109,8 @@ struct View {
     int* cnt_i;           // [n_slots][N2] kept points per cell
     int* raw_i;           // [n_slots][N2] inside points per cell (full layers)
     int* cellstart;       // [n_slots][N2] exclusive scan of cnt_i
-    int* sort_hist;       // [n_slots][digits * sort_blocks]
+    int* sort_hist;       // [n_slots][digits * sort_blocks] pass 1 (low digit): per-tile histogram -> offsets
+    int* sort_hist2;      // same for pass 2 (high digit); filled by the pass-1 scatter with atomics
     uint32_t* out_index;  // [n_slots][pcap]
     int* out_counts;      // [n_slots][3 * out_blocks + 1]  (+1: n_out)
     gg_point* out_cloud;  // [n_slots][pcap] (allocated lazily)
@@ -137,8 +138,7 @@ constexpr int OUT_TILE = 1024;
 
 // kernels of the pipeline, as reported by the profiling hooks (gg_profile_read)
 enum KernelId : int {
-    K_CLEAR = 0, K_RASTERIZE, K_SORT_HIST1, K_SORT_SCAN1, K_SORT_SCATTER1, K_SORT_HIST2, K_SORT_SCAN2, K_SORT_SCATTER2,
-    K_SCAN_CELLS, K_CELL_STATS, K_DETECT, K_SPIRAL, K_LABEL, K_ROLL_GATHER, K_ROLL_COMMIT, K_OUT_COUNT, K_OUT_SCAN,
+    K_RASTERIZE = 0, K_SCAN_LO_CELLS, K_SORT_SCATTER1, K_SORT_SCAN2, K_SORT_SCATTER2, K_CELL_STATS, K_DETECT, K_SPIRAL, K_LABEL, K_ROLL_GATHER, K_ROLL_COMMIT, K_OUT_COUNT, K_OUT_SCAN,
     K_OUT_WRITE, K_NUM
 };
 

@@ -172,25 +172,10 @@ __global__ void __launch_bounds__(256) k_roll_commit(View v, const SlotParams* _
     v.layer(sp.slot, L_GROUNDPATCH)[cell] = sg[v.k.N2 + cell];
 }
 
-// per-scan reset of the accumulators that are built with atomics (the float layers are fully
-// rewritten by k_cell_stats, which replaces the fills of GroundSegmentation.cpp:61-75)
-__global__ void __launch_bounds__(256) k_clear_scan(View v, const SlotParams* __restrict__ batch) {
-    const SlotParams& sp = batch[blockIdx.y];
-    const int cell = blockIdx.x * 256 + threadIdx.x;
-    if (cell >= v.k.N2) return;
-    const size_t off = (size_t)sp.slot * v.k.N2;
-    v.cnt_i[off + cell] = 0;
-    if (v.k.full_layers) v.raw_i[off + cell] = 0;
-    v.layer(sp.slot, L_OBSTACLES)[cell] = 0.0f;  // map["points"].setConstant(0.0), :147
-}
-
 // ------------------------------------------------------------------------------------------
 // phase 1a: per-point rasterisation front end (insert_cloud up to the accumulate step)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_rasterize(View v, const SlotParams* __restrict__ batch) {
-    const SlotParams& sp = batch[blockIdx.y];
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= sp.n_points) return;
+__device__ __forceinline__ uint32_t rasterize_point(const View& v, const SlotParams& sp, int i) {
     const Const& k = v.k;
     const int N = k.N;
     const size_t base = (size_t)sp.slot * v.pcap;
@@ -280,37 +265,54 @@ __global__ void __launch_bounds__(256) k_rasterize(View v, const SlotParams* __r
     }
     v.key[base + i] = key;
     v.code[base + i] = code;
+    return key;
+}
+
+// One block = one sort tile (SORT_TILE consecutive points, SORT_THREADS threads): besides the
+// per-point products it leaves the tile's histogram of the LOW key digit (pass 1 of the radix sort
+// needs no separate counting pass) and clears its column of the high-digit table.
+__global__ void __launch_bounds__(SORT_THREADS) k_rasterize(View v, const SlotParams* __restrict__ batch, int nb) {
+    extern __shared__ int s_hist[];
+    const SlotParams& sp = batch[blockIdx.y];
+    const int D = 1 << v.bits_lo, D2 = 1 << v.bits_hi;
+    for (int d = threadIdx.x; d < D; d += SORT_THREADS) s_hist[d] = 0;
+    __syncthreads();
+    const int n = sp.n_points;
+    const int tile0 = blockIdx.x * SORT_TILE;
+    const uint32_t mask = (uint32_t)D - 1u;
+    for (int r = 0; r < SORT_TILE / SORT_THREADS; ++r) {
+        const int i = tile0 + r * SORT_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&s_hist[rasterize_point(v, sp, i) & mask], 1);
+    }
+    __syncthreads();
+    const size_t hoff = (size_t)sp.slot * ((size_t)v.sort_blocks << max(v.bits_lo, v.bits_hi));
+    int* hist = v.sort_hist + hoff;
+    for (int d = threadIdx.x; d < D; d += SORT_THREADS) hist[d * nb + blockIdx.x] = s_hist[d];
+    int* hist2 = v.sort_hist2 + hoff;
+    for (int d = threadIdx.x; d < D2; d += SORT_THREADS) hist2[d * nb + blockIdx.x] = 0;
 }
 
 // ------------------------------------------------------------------------------------------
 // phase 1b: stable LSD radix sort (cell -> z), two passes
 // ------------------------------------------------------------------------------------------
-// per-block digit histogram; hist layout [slot][digit * nb + block]
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(View v, const SlotParams* __restrict__ batch, const uint32_t* __restrict__ keys,
-                                                            int shift, int bits, int nb) {
-    extern __shared__ int s_hist[];
-    const SlotParams& sp = batch[blockIdx.y];
-    const int D = 1 << bits;
-    for (int d = threadIdx.x; d < D; d += SORT_THREADS) s_hist[d] = 0;
-    __syncthreads();
-    const int n = sp.n_points;
-    const uint32_t* kin = keys + (size_t)sp.slot * v.pcap;
-    const int tile0 = blockIdx.x * SORT_TILE;
-    const uint32_t mask = (uint32_t)D - 1u;
-#pragma unroll
-    for (int r = 0; r < SORT_TILE / SORT_THREADS; ++r) {
-        const int idx = tile0 + r * SORT_THREADS + threadIdx.x;
-        if (idx < n) atomicAdd(&s_hist[(kin[idx] >> shift) & mask], 1);
+// hist layout [slot][digit * nb + tile].  Blocks [0, count) scan the low-digit table of the sort,
+// blocks [count, 2 count) the per-cell kept counts (both only depend on k_rasterize).
+__global__ void __launch_bounds__(1024) k_scan_lo_cells(View v, const SlotParams* __restrict__ batch, int count, int nb) {
+    const bool cells = (int)blockIdx.x >= count;
+    const SlotParams& sp = batch[cells ? blockIdx.x - count : blockIdx.x];
+    if (cells) {
+        const size_t off = (size_t)sp.slot * v.k.N2;
+        block_exclusive_scan_1024(v.cnt_i + off, v.cellstart + off, v.k.N2);
+    } else {
+        int* hist = v.sort_hist + (size_t)sp.slot * ((size_t)v.sort_blocks << max(v.bits_lo, v.bits_hi));
+        block_exclusive_scan_1024(hist, hist, nb << v.bits_lo);
     }
-    __syncthreads();
-    int* hist = v.sort_hist + (size_t)sp.slot * ((size_t)v.sort_blocks << max(v.bits_lo, v.bits_hi));
-    for (int d = threadIdx.x; d < D; d += SORT_THREADS) hist[d * nb + blockIdx.x] = s_hist[d];
 }
 
-__global__ void __launch_bounds__(1024) k_sort_scan(View v, const SlotParams* __restrict__ batch, int bits, int nb) {
+__global__ void __launch_bounds__(1024) k_sort_scan_hi(View v, const SlotParams* __restrict__ batch, int nb) {
     const SlotParams& sp = batch[blockIdx.x];
-    int* hist = v.sort_hist + (size_t)sp.slot * ((size_t)v.sort_blocks << max(v.bits_lo, v.bits_hi));
-    block_exclusive_scan_1024(hist, hist, nb << bits);
+    int* hist = v.sort_hist2 + (size_t)sp.slot * ((size_t)v.sort_blocks << max(v.bits_lo, v.bits_hi));
+    block_exclusive_scan_1024(hist, hist, nb << v.bits_hi);
 }
 
 // Stable scatter.  A block owns SORT_TILE consecutive items and walks them in rounds of
@@ -366,24 +368,23 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(View v, const Slo
         }
         my_rank[r] = basecnt + rank_in_warp;
     }
-    const int* offs = v.sort_hist + (size_t)sp.slot * ((size_t)v.sort_blocks << max(v.bits_lo, v.bits_hi));
+    const size_t hoff = (size_t)sp.slot * ((size_t)v.sort_blocks << max(v.bits_lo, v.bits_hi));
+    const int* offs = (LAST ? v.sort_hist2 : v.sort_hist) + hoff;
+    int* hist2 = v.sort_hist2 + hoff;
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
         const int idx = tile0 + r * SORT_THREADS + threadIdx.x;
         if (idx < n) {
             const int d = (int)((my_key[r] >> shift) & mask);
             const int pos = offs[d * nb + blockIdx.x] + my_rank[r];
-            if (!LAST) keys_out[base + pos] = my_key[r];
+            if (!LAST) {
+                keys_out[base + pos] = my_key[r];
+                // histogram of the next pass: high digit x destination tile
+                atomicAdd(&hist2[(int)(my_key[r] >> bits) * nb + pos / SORT_TILE], 1);
+            }
             vals_out[base + pos] = my_val[r];
         }
     }
-}
-
-// exclusive scan of the per-cell kept counts -> start of every cell's run in zsorted
-__global__ void __launch_bounds__(1024) k_scan_cells(View v, const SlotParams* __restrict__ batch) {
-    const SlotParams& sp = batch[blockIdx.x];
-    const size_t off = (size_t)sp.slot * v.k.N2;
-    block_exclusive_scan_1024(v.cnt_i + off, v.cellstart + off, v.k.N2);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -429,6 +430,8 @@ __global__ void __launch_bounds__(128) k_cell_stats(View v, const SlotParams* __
             n = __fadd_rn(n, 1.0f);
         }
     }
+    v.cnt_i[coff + cell] = 0;                      // consumed: zero again for the next scan
+    v.layer(sp.slot, L_OBSTACLES)[cell] = 0.0f;    // map["points"].setConstant(0.0), :147 (k_label counts into it)
     v.layer(sp.slot, L_COUNT)[cell] = n;
     v.layer(sp.slot, L_VARIANCE)[cell] = __fdiv_rn(m2, __fadd_rn(n, FLT_MIN));
     v.layer(sp.slot, L_MINH)[cell] = mn;
@@ -439,6 +442,7 @@ __global__ void __launch_bounds__(128) k_cell_stats(View v, const SlotParams* __
         v.layer(sp.slot, L_PLANEDIST)[cell] = pdm;
         v.layer(sp.slot, L_MAXH)[cell] = mx;
         v.layer(sp.slot, L_RAW)[cell] = (float)v.raw_i[coff + cell];
+        v.raw_i[coff + cell] = 0;
     }
 }
 
@@ -1172,24 +1176,18 @@ int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int 
     const int pblocks = max(1, cdiv(max_points, 256));
     const int nb = max(1, cdiv(max_points, SORT_TILE));
 
-    GG_LAUNCH(K_CLEAR, k_clear_scan<<<dim3(cdiv(N2, 256), count), 256, 0, st>>>(v, batch));
-    GG_LAUNCH(K_RASTERIZE, k_rasterize<<<dim3(pblocks, count), 256, 0, st>>>(v, batch));
-    launches += 2;
-
-    // pass 1: low digit, (key, zval) -> (key2, z2)
+    // radix sort, pass 1 (low digit): the tile histograms come out of k_rasterize itself
     size_t sh = sizeof(int) << v.bits_lo;
-    GG_LAUNCH(K_SORT_HIST1, k_sort_hist<<<dim3(nb, count), SORT_THREADS, sh, st>>>(v, batch, v.key, 0, v.bits_lo, nb));
-    GG_LAUNCH(K_SORT_SCAN1, k_sort_scan<<<count, 1024, 0, st>>>(v, batch, v.bits_lo, nb));
+    GG_LAUNCH(K_RASTERIZE, k_rasterize<<<dim3(nb, count), SORT_THREADS, sh, st>>>(v, batch, nb));
+    GG_LAUNCH(K_SCAN_LO_CELLS, k_scan_lo_cells<<<2 * count, 1024, 0, st>>>(v, batch, count, nb));
     GG_LAUNCH(K_SORT_SCATTER1,
               k_sort_scatter<false><<<dim3(nb, count), SORT_THREADS, sh, st>>>(v, batch, v.key, v.zval, v.key2, v.z2, 0, v.bits_lo, nb));
-    // pass 2: high digit, (key2, z2) -> zsorted
+    // pass 2 (high digit): its histogram was accumulated by the pass-1 scatter; (key2, z2) -> zsorted
     sh = sizeof(int) << v.bits_hi;
-    GG_LAUNCH(K_SORT_HIST2, k_sort_hist<<<dim3(nb, count), SORT_THREADS, sh, st>>>(v, batch, v.key2, v.bits_lo, v.bits_hi, nb));
-    GG_LAUNCH(K_SORT_SCAN2, k_sort_scan<<<count, 1024, 0, st>>>(v, batch, v.bits_hi, nb));
+    GG_LAUNCH(K_SORT_SCAN2, k_sort_scan_hi<<<count, 1024, 0, st>>>(v, batch, nb));
     GG_LAUNCH(K_SORT_SCATTER2, k_sort_scatter<true><<<dim3(nb, count), SORT_THREADS, sh, st>>>(v, batch, v.key2, v.z2, nullptr, v.zsorted,
                                                                                              v.bits_lo, v.bits_hi, nb));
-    GG_LAUNCH(K_SCAN_CELLS, k_scan_cells<<<count, 1024, 0, st>>>(v, batch));
-    launches += 7;
+    launches += 5;
 
     if (v.k.full_layers)
         GG_LAUNCH(K_CELL_STATS, k_cell_stats<true><<<dim3(cdiv(N2, 128), count), 128, 0, st>>>(v, batch));
