@@ -93,6 +93,10 @@ def load(build_if_missing=True):
         "gg_download_labels": (i, [vp, i, vp, sz]),
         "gg_synchronize": (i, [vp]),
         "gg_run_scans_device": (i, [vp, i, vp, vp, i]),
+        "gg_upload_cloud_msg": (i, [vp, i, vp, sz, i, vp, vp]),
+        "gg_terrain_image": (i, [vp, i, vp]),
+        "gg_eval_accumulate": (i, [vp, i]),
+        "gg_eval_read": (i, [vp, vp, i]),
         "gg_profile_enable": (i, [vp, i]),
         "gg_profile_read": (i, [vp, vp, vp, i]),
         "gg_profile_kernel_count": (i, []),
@@ -307,6 +311,28 @@ class GroundGridB200:
         """dev_ptrs: device addresses (ints) of the per-scan clouds (32-byte records)."""
         pp = (C.c_void_p * len(descs))(*dev_ptrs)
         _check(self._l.gg_run_scans_device(self._h, len(descs), descs, pp, stop_after))
+
+    # -- steps next to the path (SURVEY section 8f)
+    def upload_cloud_msg(self, raw, n_points, point_step, field_offsets, T_map_from_frame=None, slot=0):
+        """raw: uint8 array of the PointCloud2 payload; field_offsets: x, y, z, intensity, ring (-1 absent)."""
+        raw = np.ascontiguousarray(raw, np.uint8)
+        off = np.ascontiguousarray(field_offsets, np.int32)
+        T = None if T_map_from_frame is None else np.ascontiguousarray(T_map_from_frame, np.float64).reshape(12)
+        _check(self._l.gg_upload_cloud_msg(self._h, slot, _ptr(raw), int(n_points), int(point_step), _ptr(off), _ptr(T)))
+        return raw
+
+    def terrain_image(self, slot=0):
+        img = np.zeros((self.n, self.n, 3), np.float32)
+        _check(self._l.gg_terrain_image(self._h, slot, _ptr(img)))
+        return img
+
+    def eval_accumulate(self, slot=0):
+        _check(self._l.gg_eval_accumulate(self._h, slot))
+
+    def eval_read(self, reset=False):
+        counts = np.zeros((1024, 2), np.uint64)
+        _check(self._l.gg_eval_read(self._h, _ptr(counts), 1 if reset else 0))
+        return counts
 
     def profile_enable(self, on=True):
         _check(self._l.gg_profile_enable(self._h, 1 if on else 0))

@@ -229,6 +229,10 @@ struct gg_handle_s {
     std::vector<void*> dev_allocs;
     int sched_levels = 0, sched_visits = 0, sched_max = 0;
     bool out_cloud_ready = false;
+    unsigned char* d_raw = nullptr;  // f1: device copy of a PointCloud2 payload
+    size_t d_raw_cap = 0;
+    float* d_image = nullptr;        // f3: terrain image staging (N * N * 3)
+    unsigned long long* d_eval = nullptr;  // f4: [EVAL_LABELS][2] tallies
     HostPacker* packer = nullptr;    // created on the first packed batch call
     unsigned char* h_packed = nullptr;  // pinned staging, [n_slots][14 * pcap]
     int host_pack = 1;               // GG_HOST_PACK=0 sends the 32-byte records as they are
@@ -646,6 +650,7 @@ int gg_destroy(gg_handle h) {
     cudaDeviceSynchronize();
     delete h->prof;
     delete h->packer;
+    if (h->d_raw) cudaFree(h->d_raw);
     if (h->h_packed) cudaFreeHost(h->h_packed);
     for (void* p : h->dev_allocs) cudaFree(p);
     if (h->h_ring) cudaFreeHost(h->h_ring);
@@ -791,6 +796,99 @@ int gg_run_scans_device(gg_handle h, int count, const gg_scan_desc* scans, const
     return run_scans_grouped(h, count, scans, stop_after, dev_points);
 }
 
+// ---- "next" rows of SURVEY.md section 8(f) --------------------------------------------------
+int gg_upload_cloud_msg(gg_handle h, int slot, const void* data, size_t n_points, int point_step, const int field_offsets[5],
+                        const double T_map_from_frame[12]) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    if (n_points > h->pcap) return fail(GG_E_ARG, "%zu points exceed capacity %zu", n_points, h->pcap);
+    if ((n_points && !data) || !field_offsets || point_step < 12) return fail(GG_E_ARG, "bad PointCloud2 layout");
+    for (int f = 0; f < 5; ++f) {
+        const int width = f == 4 ? 2 : 4;
+        if ((f < 3 && field_offsets[f] < 0) || field_offsets[f] + width > point_step) return fail(GG_E_ARG, "field %d does not fit point_step", f);
+    }
+    GG_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream_of(h, slot);
+    const size_t bytes = n_points * (size_t)point_step;
+    if (bytes > h->d_raw_cap) {
+        GG_CUDA(cudaStreamSynchronize(st));
+        if (h->d_raw) GG_CUDA(cudaFree(h->d_raw));
+        h->d_raw = nullptr;
+        h->d_raw_cap = 0;
+        GG_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_raw), bytes + 256));
+        h->d_raw_cap = bytes;
+    }
+    if (bytes) GG_CUDA(cudaMemcpyAsync(h->d_raw, data, bytes, cudaMemcpyHostToDevice, st));
+    gg::UnpackDesc d;
+    std::memset(&d, 0, sizeof(d));
+    d.raw = h->d_raw;
+    d.dst = h->view.points + (size_t)slot * h->pcap;
+    d.n = (int)n_points;
+    d.point_step = point_step;
+    for (int f = 0; f < 5; ++f) d.off[f] = field_offsets[f];
+    d.transform = T_map_from_frame ? 1 : 0;
+    if (T_map_from_frame) std::memcpy(d.T, T_map_from_frame, sizeof(d.T));
+    h->launches += gg::launch_unpack(d, st, h->prof);
+    GG_CUDA(cudaGetLastError());
+    h->slots[slot].n_points = n_points;
+    return GG_OK;
+}
+
+int gg_terrain_image(gg_handle h, int slot, float* dst) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    if (!dst) return fail(GG_E_ARG, "null dst");
+    if (!(h->flags & GG_FLAG_FULL_LAYERS)) return fail(GG_E_LAYER, "the terrain image needs 'pointsRaw' (GG_FLAG_FULL_LAYERS)");
+    GG_CUDA(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->view.k.N2 * 3;
+    if (!h->d_image && (rc = dev_alloc(h, &h->d_image, n))) return rc;
+    cudaStream_t st = stream_of(h, slot);
+    h->launches += gg::launch_terrain_image(h->view, slot, h->d_image, st, h->prof);
+    GG_CUDA(cudaGetLastError());
+    GG_CUDA(cudaMemcpyAsync(dst, h->d_image, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    GG_CUDA(cudaStreamSynchronize(st));
+    return GG_OK;
+}
+
+int gg_eval_accumulate(gg_handle h, int slot) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    SlotState& s = h->slots[slot];
+    if (!s.ran || s.last_stop != 0) return fail(GG_E_STATE, "slot %d: no completed scan", slot);
+    GG_CUDA(cudaSetDevice(h->device));
+    if (!h->d_eval) {
+        if ((rc = dev_alloc(h, &h->d_eval, (size_t)gg::EVAL_LABELS * 2))) return rc;
+        GG_CUDA(cudaMemset(h->d_eval, 0, sizeof(unsigned long long) * gg::EVAL_LABELS * 2));
+    }
+    cudaStream_t st = stream_of(h, slot);
+    gg::SlotParams *hp = nullptr, *dp = nullptr;
+    int pos = 0;
+    if ((rc = ring_acquire(h, &hp, &dp, &pos))) return rc;
+    std::memset(&hp[0], 0, sizeof(gg::SlotParams));
+    hp[0].slot = slot;
+    hp[0].n_points = (int)s.n_points;
+    hp[0].src = s.src ? s.src : h->view.points + (size_t)slot * h->pcap;
+    hp[0].packed = s.packed_input ? reinterpret_cast<const float*>(h->view.packed + (size_t)slot * 14 * h->pcap) : nullptr;
+    if ((rc = ring_commit(h, pos, 1, st))) return rc;
+    h->launches += gg::launch_eval(h->view, dp, h->d_eval, st, h->prof);
+    GG_CUDA(cudaGetLastError());
+    return ring_release(h, pos, st);
+}
+
+int gg_eval_read(gg_handle h, uint64_t* counts, int reset) {
+    if (!h || !counts) return fail(GG_E_ARG, "null argument");
+    int rc = gg_synchronize(h);
+    if (rc) return rc;
+    const size_t bytes = sizeof(unsigned long long) * gg::EVAL_LABELS * 2;
+    if (!h->d_eval) {
+        std::memset(counts, 0, bytes);
+        return GG_OK;
+    }
+    GG_CUDA(cudaMemcpy(counts, h->d_eval, bytes, cudaMemcpyDeviceToHost));
+    if (reset) GG_CUDA(cudaMemset(h->d_eval, 0, bytes));
+    return GG_OK;
+}
+
 int gg_profile_enable(gg_handle h, int on) {
     if (!h) return fail(GG_E_ARG, "null handle");
     GG_CUDA(cudaSetDevice(h->device));
@@ -826,7 +924,8 @@ int gg_profile_kernel_count(void) { return gg::K_NUM; }
 const char* gg_profile_kernel_name(int id) {
     static const char* names[gg::K_NUM] = {"k_rasterize",   "k_scan_lo_cells", "k_sort_scatter(lo)", "k_sort_scan(hi)", "k_sort_scatter(hi)",
                                            "k_cell_stats",  "k_detect",        "k_spiral",           "k_label",         "k_roll_gather",
-                                           "k_roll_commit", "k_out_count",     "k_out_scan",         "k_out_write"};
+                                           "k_roll_commit", "k_out_count",     "k_out_scan",         "k_out_write",     "k_unpack_transform",
+                                           "k_terrain_image", "k_eval_counts"};
     return (id >= 0 && id < gg::K_NUM) ? names[id] : "";
 }
 

@@ -139,7 +139,7 @@ constexpr int OUT_TILE = 1024;
 // kernels of the pipeline, as reported by the profiling hooks (gg_profile_read)
 enum KernelId : int {
     K_RASTERIZE = 0, K_SCAN_LO_CELLS, K_SORT_SCATTER1, K_SORT_SCAN2, K_SORT_SCATTER2, K_CELL_STATS, K_DETECT, K_SPIRAL, K_LABEL, K_ROLL_GATHER, K_ROLL_COMMIT, K_OUT_COUNT, K_OUT_SCAN,
-    K_OUT_WRITE, K_NUM
+    K_OUT_WRITE, K_UNPACK, K_TERRAIN, K_EVAL, K_NUM
 };
 
 // Optional per-kernel CUDA-event timing (bench.py's roofline needs the dominant kernel's own
@@ -158,5 +158,18 @@ int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int 
                          Profiler* prof);
 int launch_output(const View& v, const SlotParams* batch, int count, int max_points, bool want_cloud, cudaStream_t st,
                   Profiler* prof);
+// "next" rows of SURVEY.md section 8(f)
+struct UnpackDesc {   // f1: PointCloud2 payload -> PointXYZIR records in the map frame
+    const unsigned char* raw;  // device copy of msg.data
+    gg_point* dst;
+    int n, point_step;
+    int off[5];                // byte offsets of x, y, z, intensity, ring (-1: field absent)
+    int transform;             // 0: frame_id == "map", copy only
+    double T[12];              // row-major 3x4 [R|t] of lookupTransform("map", frame_id)
+};
+int launch_unpack(const UnpackDesc& d, cudaStream_t st, Profiler* prof);
+int launch_terrain_image(const View& v, int slot, float* dst, cudaStream_t st, Profiler* prof);
+int launch_eval(const View& v, const SlotParams* batch, unsigned long long* counts, cudaStream_t st, Profiler* prof);
+constexpr int EVAL_LABELS = 1024;  // ring values (SemanticKITTI label ids <= 259) x {ground, non-ground}
 
 }  // namespace gg

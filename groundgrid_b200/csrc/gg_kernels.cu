@@ -1123,6 +1123,80 @@ __global__ void __launch_bounds__(OUT_TILE) k_out_write(View v, const SlotParams
 }
 
 // ------------------------------------------------------------------------------------------
+// "next" rows
+// ------------------------------------------------------------------------------------------
+// f1: pcl::fromROSMsg (field-offset driven unpack, GroundGridNodelet.cpp:119-120) + the per-point
+// tf2::doTransform into the map frame in fp64, stored as float (:166-181).
+__global__ void __launch_bounds__(256) k_unpack_transform(UnpackDesc d) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= d.n) return;
+    const unsigned char* p = d.raw + (size_t)i * d.point_step;
+    auto rd32 = [&](int off) -> uint32_t {
+        if (off < 0) return 0u;
+        return (uint32_t)p[off] | ((uint32_t)p[off + 1] << 8) | ((uint32_t)p[off + 2] << 16) | ((uint32_t)p[off + 3] << 24);
+    };
+    float x = __uint_as_float(rd32(d.off[0])), y = __uint_as_float(rd32(d.off[1])), z = __uint_as_float(rd32(d.off[2]));
+    const uint32_t inten = rd32(d.off[3]);
+    const uint32_t ring = d.off[4] < 0 ? 0u : ((uint32_t)p[d.off[4]] | ((uint32_t)p[d.off[4] + 1] << 8));
+    if (d.transform) {
+        const double dx = (double)x, dy = (double)y, dz = (double)z;
+        // tf2::Transform * Vector3: row.dot(v) (left to right) + origin
+        x = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(d.T[0], dx), __dmul_rn(d.T[1], dy)), __dmul_rn(d.T[2], dz)), d.T[3]);
+        y = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(d.T[4], dx), __dmul_rn(d.T[5], dy)), __dmul_rn(d.T[6], dz)), d.T[7]);
+        z = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(d.T[8], dx), __dmul_rn(d.T[9], dy)), __dmul_rn(d.T[10], dz)), d.T[11]);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(d.dst + i);
+    dst[0] = make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(z), 0u);
+    dst[1] = make_uint4(inten, ring, 0u, 0u);
+}
+
+// f3: the "terrain" image of GroundGridNodelet::publish_grid_map_layer (:247-270): CV_32FC3, pixel
+// (i, j) = (ground height, 3x3 sum of pointsRaw >= 27 ? 1 : 0, pointsRaw).  The reference reads the
+// 3x3 block out of bounds on the border cells; here border cells get visited = 0.
+__global__ void __launch_bounds__(256) k_terrain_image(View v, int slot, float* __restrict__ dst) {
+    const int cell = blockIdx.x * 256 + threadIdx.x;
+    if (cell >= v.k.N2) return;
+    const int N = v.k.N;
+    const int i = cell % N, j = cell / N;
+    const float* raw = v.layer(slot, L_RAW);
+    float visited = 0.0f;
+    if (i >= 1 && j >= 1 && i < N - 1 && j < N - 1) {
+        float e[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) e[q] = raw[(i - 1 + q % 3) + (j - 1 + q / 3) * N];
+        visited = tree9(e) >= 27.0f ? 1.0f : 0.0f;
+    }
+    float* px = dst + ((size_t)i * N + j) * 3;  // cv::Mat row = index(0), col = index(1)
+    px[0] = v.layer(slot, L_GROUND)[cell];
+    px[1] = visited;
+    px[2] = raw[cell];
+}
+
+// f4: the tallies of scripts/eval_groundpoint_classifier.py:95-118 for one segmented cloud: per
+// ground-truth label id (carried in `ring`, scripts/kitti_data_publisher.py:122-132) the number of
+// points predicted non-ground (intensity 99) and ground (49).
+__global__ void __launch_bounds__(256) k_eval_counts(View v, const SlotParams* __restrict__ batch, unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int s_cnt[EVAL_LABELS * 2];
+    for (int t = threadIdx.x; t < EVAL_LABELS * 2; t += 256) s_cnt[t] = 0u;
+    __syncthreads();
+    const SlotParams& sp = batch[0];
+    const size_t base = (size_t)sp.slot * v.pcap;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < sp.n_points; i += gridDim.x * 256) {
+        const unsigned label = v.labels[base + i];
+        if (label == GG_LABEL_ABSENT) continue;
+        unsigned ring;
+        if (sp.packed)
+            ring = reinterpret_cast<const unsigned short*>(sp.packed + 3 * ((sp.n_points + 7) & ~7))[i];
+        else
+            ring = reinterpret_cast<const uint4*>(sp.src + i)[1].y & 0xffffu;
+        if (ring < EVAL_LABELS) atomicAdd(&s_cnt[ring * 2 + (label == GG_LABEL_NONGROUND ? 1 : 0)], 1u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < EVAL_LABELS * 2; t += 256)
+        if (s_cnt[t]) atomicAdd(&counts[t], (unsigned long long)s_cnt[t]);
+}
+
+// ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -1242,6 +1316,21 @@ int launch_output(const View& v, const SlotParams* batch, int count, int max_poi
     else
         GG_LAUNCH(K_OUT_WRITE, k_out_write<false><<<dim3(nblk, count), OUT_TILE, 0, st>>>(v, batch, nblk));
     return 3;
+}
+
+int launch_unpack(const UnpackDesc& d, cudaStream_t st, Profiler* prof) {
+    GG_LAUNCH(K_UNPACK, k_unpack_transform<<<max(1, cdiv(d.n, 256)), 256, 0, st>>>(d));
+    return 1;
+}
+
+int launch_terrain_image(const View& v, int slot, float* dst, cudaStream_t st, Profiler* prof) {
+    GG_LAUNCH(K_TERRAIN, k_terrain_image<<<cdiv(v.k.N2, 256), 256, 0, st>>>(v, slot, dst));
+    return 1;
+}
+
+int launch_eval(const View& v, const SlotParams* batch, unsigned long long* counts, cudaStream_t st, Profiler* prof) {
+    GG_LAUNCH(K_EVAL, k_eval_counts<<<148, 256, 0, st>>>(v, batch, counts));
+    return 1;
 }
 
 }  // namespace gg

@@ -168,6 +168,27 @@ int gg_synchronize(gg_handle h);
  * must stay valid until the work is complete (and until gg_get_output, if that is used). */
 int gg_run_scans_device(gg_handle h, int count, const gg_scan_desc* scans, const gg_point* const* dev_points, int stop_after);
 
+/* ---- steps next to the path -------------------------------------------
+ * gg_upload_cloud_msg replaces pcl::fromROSMsg + the per-point tf2::doTransform loop of
+ * GroundGridNodelet::points_callback (src/GroundGridNodelet.cpp:119-120,148-184): the raw
+ * sensor_msgs/PointCloud2 payload (`point_step` bytes per point, fields x, y, z, intensity float32 and
+ * ring uint16 at `field_offsets`, -1 = absent; e.g. {0,4,8,12,16} for the KITTI player's 18-byte points,
+ * scripts/kitti_data_publisher.py:139-150) is copied to the device, unpacked into PointXYZIR records
+ * and -- unless T is NULL (frame_id == "map") -- transformed with the row-major 3x4 T = lookupTransform
+ * ("map", frame_id) in fp64.  The records land in the slot's cloud buffer: follow with gg_run_scans.
+ *
+ * gg_terrain_image replaces the "terrain" branch of publish_grid_map_layer (:247-270): N*N*3 floats,
+ * pixel (i, j) = (ground, 3x3 pointsRaw sum >= 27 ? 1 : 0, pointsRaw); needs GG_FLAG_FULL_LAYERS.
+ *
+ * gg_eval_accumulate / gg_eval_read replace the tallies of scripts/eval_groundpoint_classifier.py:95-118:
+ * counts[id][0] / counts[id][1] = points of ground-truth label `id` (taken from `ring`) predicted ground /
+ * non-ground, accumulated over the scans it was called for (1024 ids). */
+int gg_upload_cloud_msg(gg_handle h, int slot, const void* data, size_t n_points, int point_step, const int field_offsets[5],
+                        const double T_map_from_frame[12]);
+int gg_terrain_image(gg_handle h, int slot, float* dst);
+int gg_eval_accumulate(gg_handle h, int slot);
+int gg_eval_read(gg_handle h, uint64_t* counts, int reset);
+
 /* Per-kernel CUDA-event timing on the launching stream (bench.py roofline).  While enabled every
  * kernel launch is bracketed by an event pair; gg_profile_read synchronises and returns the
  * accumulated milliseconds and launch counts per kernel id (arrays of gg_profile_kernel_count()). */

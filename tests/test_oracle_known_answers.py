@@ -316,3 +316,27 @@ def test_flat_patch_groundlevel_exact():
     g = o.layer("ground")[i0, j0]
     c = o.layer("groundpatch")[i0, j0]
     assert 0.0 < g < 0.14 and c > 0.25
+
+
+def test_next_row_restatements_by_hand():
+    """oracle/nextrows.py: tiny hand-checkable cases of the steps next to the path."""
+    from oracle import nextrows
+
+    # f1: one 18-byte point (KITTI player layout), translation + 90 degree yaw
+    raw = np.zeros((1, 18), np.uint8)
+    raw[0, 0:4] = np.frombuffer(np.float32(1.0).tobytes(), np.uint8)
+    raw[0, 4:8] = np.frombuffer(np.float32(2.0).tobytes(), np.uint8)
+    raw[0, 8:12] = np.frombuffer(np.float32(3.0).tobytes(), np.uint8)
+    raw[0, 12:16] = np.frombuffer(np.float32(0.5).tobytes(), np.uint8)
+    raw[0, 16:18] = np.frombuffer(np.uint16(40).tobytes(), np.uint8)
+    T = np.array([[0.0, -1.0, 0.0, 10.0], [1.0, 0.0, 0.0, 20.0], [0.0, 0.0, 1.0, 30.0]])
+    p = nextrows.unpack_transform(raw, 1, 18, (0, 4, 8, 12, 16), T)
+    assert (p["x"][0], p["y"][0], p["z"][0], p["intensity"][0], p["ring"][0]) == (8.0, 21.0, 33.0, 0.5, 40)
+    # f3: visited flag = 3x3 sum of pointsRaw >= 27
+    raw_cnt = np.zeros((6, 6), np.float32)
+    raw_cnt[1:4, 1:4] = 3.0
+    img = nextrows.terrain_image(np.full((6, 6), 0.25, np.float32), raw_cnt)
+    assert img[2, 2, 1] == 1.0 and img[2, 3, 1] == 0.0 and img[0, 0, 1] == 0.0 and img[2, 2, 2] == 3.0 and img[5, 5, 0] == 0.25
+    # f4: tallies per ground-truth id; absent points do not count
+    c = nextrows.eval_counts(np.array([49, 99, 49, 0, 99], np.uint8), np.array([40, 40, 10, 10, 10], np.uint16))
+    assert tuple(c[40]) == (1, 1) and tuple(c[10]) == (1, 1) and c.sum() == 4
