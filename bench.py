@@ -83,7 +83,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -270,7 +270,9 @@ def main():
         for s in range(S):
             offs[b, s] = total
             total += int(npts[b, s]) * 32
-    host_pool = torch.empty(total, dtype=torch.uint8).pin_memory()
+    host_pool = torch.empty(total, dtype=torch.uint8)
+    if not args.no_e2e:
+        host_pool = host_pool.pin_memory()
     hp = host_pool.numpy()
     for b in range(B):
         for s in range(S):
@@ -360,7 +362,7 @@ def main():
     # ---- end to end through the host-buffer C-ABI call
     e2e = None
     if not args.no_e2e:
-        for _ in range(2):
+        for _ in range(6):     # also lets the library settle on packed vs plain H2D (it measures both, twice each)
             step_e2e()
         barrier()
         t0 = time.perf_counter()
@@ -369,14 +371,14 @@ def main():
         for _ in range(args.steps):
             s = step_e2e()
             pts_e2e += int(pts_per_pose[s])
-            h2d = int(pts_per_pose[s]) * (14 if g.host_pack_threads else 32)
+            h2d = int(pts_per_pose[s]) * (14 if g.host_pack_threads > 0 else 32)
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": sum_over_ranks(pts_e2e) / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(h2d)),
                "d2h_bytes_per_step": int(sum_over_ranks(int(pts_per_pose.max()))), "ms_per_step": dt / args.steps * 1e3,
                "api": "gg_update_pose_batch + gg_filter_cloud_batch (pinned host PointXYZIR clouds in, labels out)",
-               "host_pack_threads": g.host_pack_threads,
-               "pcie_bytes_per_point": 14 if g.host_pack_threads else 32}
+               "host_pack_threads": max(0, g.host_pack_threads),
+               "pcie_bytes_per_point": 14 if g.host_pack_threads > 0 else 32}
 
     # ---- roofline of the dominant kernel (CUDA events around every launch, same timed region)
     P_mean = float(npts.mean())
@@ -396,7 +398,8 @@ def main():
         achieved = per_launch_bytes / (dom_ms / dom_n * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "peak_source": peak_src, "avg_launch_us": dom_ms / dom_n * 1e3,
-                    "algorithmic_bytes_per_launch": per_launch_bytes, "kernel_time_shares": shares}
+                    "algorithmic_bytes_per_launch": per_launch_bytes, "kernel_time_shares": shares,
+                    "kernel_avg_launch_us": {k: round(v[0] / v[1] * 1e3, 1) for k, v in prof.items()}}
     path_bytes = (45.0 * P_mean + 72.0 * N2 + 16.0 * N2) * B     # + roll every step
     path_gbs = path_bytes / (ms_dev / args.steps * 1e-3) / 1e9
     roofline_path = {"bound": "hbm", "algorithmic_bytes_per_step": path_bytes, "achieved": path_gbs, "peak": peak, "unit": "GB/s",

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -236,6 +237,11 @@ struct gg_handle_s {
     HostPacker* packer = nullptr;    // created on the first packed batch call
     unsigned char* h_packed = nullptr;  // pinned staging, [n_slots][14 * pcap]
     int host_pack = 1;               // GG_HOST_PACK=0 sends the 32-byte records as they are
+    // Packing only pays when enough host cores are actually available (shared hosts, CPU quotas), so
+    // unless GG_HOST_PACK / GG_HOST_THREADS pin the choice, the first batch calls measure both ways:
+    // calls 0-1 packed, calls 2-3 plain 32-byte DMA, then the faster one (seconds per point) stays.
+    int pack_tune_calls = 0;         // -1: choice pinned
+    double pack_best[2] = {1e30, 1e30};
     EventProfiler* prof = nullptr;   // non-null while profiling is enabled
     double prof_ms[gg::K_NUM] = {};
     uint32_t prof_count[gg::K_NUM] = {};
@@ -500,10 +506,8 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
     GG_TRY(dev_alloc(h, &expected, N2));
     v.expected = expected;
     GG_TRY(dev_alloc(h, &v.points, S * P));
-    GG_TRY(dev_alloc(h, &v.key, S * P));
-    GG_TRY(dev_alloc(h, &v.key2, S * P));
-    GG_TRY(dev_alloc(h, &v.zval, S * P));
-    GG_TRY(dev_alloc(h, &v.z2, S * P));
+    GG_TRY(dev_alloc(h, &v.kz, S * P));
+    GG_TRY(dev_alloc(h, &v.kz2, S * P));
     GG_TRY(dev_alloc(h, &v.zsorted, S * P));
     GG_TRY(dev_alloc(h, &v.dist, S * P));
     GG_TRY(dev_alloc(h, &v.code, S * P));
@@ -557,13 +561,36 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
             v.spiral_recs = reinterpret_cast<const uint4*>(d_rc);
             v.spiral_dist = dist;
         }
-        // skewed-layout spiral (GG_SPIRAL_SKEW=0 keeps the pipelined kernel); needs 4 * KP + 32 <= 1024 threads
+        // skewed-layout spiral (GG_SPIRAL_SKEW=0 keeps the pipelined kernel)
         std::memset(&v.skew, 0, sizeof(v.skew));
         int want_skew = 1;
         if (const char* e = getenv("GG_SPIRAL_SKEW")) want_skew = atoi(e);
         gg::SkewTables sk;
         if (want_skew) gg::build_spiral_skew(n, ls, vs, sk);
-        if (sk.ok && sk.max_irr_per_level * 9 <= 64 && sk.lanes + 64 <= 1024) {
+        // time-sharing of lane threads: the smallest M (multiple of 32) such that ring k + M of a side
+        // starts (prefetch window included) only after ring k has finished
+        // (only when one thread per lane does not fit a CTA: measured, a dedicated thread per lane is faster)
+        int M = 32, phases = 1;
+        if (sk.ok) {
+            const int kGap = 2 * 8 + 4;  // 2 * PF_FAR of k_spiral_skew + slack
+            if (4 * sk.KP + 64 <= 1024) M = sk.KP;
+            for (; M < sk.KP; M += 32) {
+                bool fits = true;
+                for (int sd = 0; sd < 4 && fits; ++sd)
+                    for (int c0 = 0; c0 + M < sk.KP && fits; ++c0) {
+                        const int a = sd * sk.KP + c0, b2 = a + M;
+                        if (sk.lane_begin[a] < sk.lane_end[a] && sk.lane_begin[b2] < sk.lane_end[b2] &&
+                            sk.lane_end[a] + kGap > sk.lane_begin[b2])
+                            fits = false;
+                    }
+                if (fits) break;
+            }
+            M = std::min(M, sk.KP);
+            phases = (sk.KP + M - 1) / M;
+            // one CTA: lane threads + the two irregular warps (one thread per (visit, neighbour))
+            if (4 * M + 64 > 1024 || sk.max_irr_per_level * 9 > 64) sk.ok = false;
+        }
+        if (sk.ok) {
             // re-layout of the irregular records: one dense block per level (see SkewView)
             const int irr_max = std::max(1, sk.max_irr_per_level);
             const int irr_words = ((irr_max * 22 + 3) / 4) * 4;
@@ -579,24 +606,35 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
                     }
                     const uint32_t ents[4] = {w[10] & 0xffffu, w[10] >> 16, w[11] & 0xffffu, w[11] >> 16};
                     for (uint32_t e : ents)
-                        if (e & 0x8000u) blk[(vv * 9 + ((e >> 10) & 15u)) * 2 + 1] = e & 1023u;
+                        if (e != 0xffffu) blk[(vv * 9 + (e >> 12)) * 2 + 1] = e & 4095u;
                     uint32_t* hd = blk + irr_max * 18 + vv * 4;
                     hd[0] = w[0];
                     hd[1] = w[12];
                     hd[2] = w[13];
                     hd[3] = w[14];
                 }
+            std::vector<int> ph_b((size_t)phases * 4 * M, 0), ph_e((size_t)phases * 4 * M, 0), ph_c((size_t)phases * 4 * M, 0);
+            for (int ph = 0; ph < phases; ++ph)
+                for (int sd = 0; sd < 4; ++sd)
+                    for (int m = 0; m < M; ++m) {
+                        const int col = ph * M + m;
+                        if (col >= sk.KP) continue;
+                        const size_t dst = ((size_t)ph * 4 + sd) * M + m;
+                        ph_b[dst] = sk.lane_begin[sd * sk.KP + col];
+                        ph_e[dst] = sk.lane_end[sd * sk.KP + col];
+                        ph_c[dst] = sk.lane_cell0[sd * sk.KP + col];
+                    }
             int *d_home = nullptr, *d_lb = nullptr, *d_le = nullptr, *d_lc = nullptr;
             uint32_t* d_irr = nullptr;
             GG_TRY(dev_alloc(h, &d_home, sk.cell_home.size()));
-            GG_TRY(dev_alloc(h, &d_lb, sk.lane_begin.size()));
-            GG_TRY(dev_alloc(h, &d_le, sk.lane_end.size()));
-            GG_TRY(dev_alloc(h, &d_lc, sk.lane_cell0.size()));
+            GG_TRY(dev_alloc(h, &d_lb, ph_b.size()));
+            GG_TRY(dev_alloc(h, &d_le, ph_e.size()));
+            GG_TRY(dev_alloc(h, &d_lc, ph_c.size()));
             GG_TRY(dev_alloc(h, &d_irr, blocks.size() + 16));
             GG_CUDA_TRY(cudaMemcpy(d_home, sk.cell_home.data(), sk.cell_home.size() * sizeof(int), cudaMemcpyHostToDevice));
-            GG_CUDA_TRY(cudaMemcpy(d_lb, sk.lane_begin.data(), sk.lane_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
-            GG_CUDA_TRY(cudaMemcpy(d_le, sk.lane_end.data(), sk.lane_end.size() * sizeof(int), cudaMemcpyHostToDevice));
-            GG_CUDA_TRY(cudaMemcpy(d_lc, sk.lane_cell0.data(), sk.lane_cell0.size() * sizeof(int), cudaMemcpyHostToDevice));
+            GG_CUDA_TRY(cudaMemcpy(d_lb, ph_b.data(), ph_b.size() * sizeof(int), cudaMemcpyHostToDevice));
+            GG_CUDA_TRY(cudaMemcpy(d_le, ph_e.data(), ph_e.size() * sizeof(int), cudaMemcpyHostToDevice));
+            GG_CUDA_TRY(cudaMemcpy(d_lc, ph_c.data(), ph_c.size() * sizeof(int), cudaMemcpyHostToDevice));
             GG_CUDA_TRY(cudaMemcpy(d_irr, blocks.data(), blocks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
             float2* d_sk = nullptr;
             float* d_sd = nullptr;
@@ -608,9 +646,11 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
             v.skew.sd = d_sd;
             v.skew.slots = sk.slots;
             v.skew.cell_home = d_home;
-            v.skew.lane_begin = d_lb;
-            v.skew.lane_end = d_le;
-            v.skew.lane_cell0 = d_lc;
+            v.skew.ph_begin = d_lb;
+            v.skew.ph_end = d_le;
+            v.skew.ph_cell0 = d_lc;
+            v.skew.M = M;
+            v.skew.phases = phases;
             v.skew.irr_blocks = reinterpret_cast<const uint4*>(d_irr);
             v.skew.irr_max = irr_max;
             v.skew.irr_chunks = irr_words / 4;
@@ -623,7 +663,10 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
         }
     }
 
-    if (const char* e = getenv("GG_HOST_PACK")) h->host_pack = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("GG_HOST_PACK")) {
+        h->host_pack = atoi(e) ? 1 : 0;
+        h->pack_tune_calls = -1;
+    }
     v.packed = nullptr;
     if (stream) {
         h->own_streams = false;
@@ -1005,11 +1048,21 @@ int gg_filter_cloud_batch(gg_handle h, int count, const gg_scan_desc* scans, con
             int local = 1;
             if (const char* e = getenv("LOCAL_WORLD_SIZE")) local = std::max(1, atoi(e));
             threads = std::min(48, gg::usable_cpus() / local - 1);
-            if (threads < 14) h->host_pack = 0;  // ~0.14 Gpts/s per packing thread vs ~1.4 Gpts/s of plain 32-byte DMA
+            if (threads < 6) {  // hopeless: ~0.14 Gpts/s per packing thread vs ~1.4 Gpts/s of plain 32-byte DMA
+                h->host_pack = 0;
+                h->pack_tune_calls = -1;
+            }
+        } else {
+            h->pack_tune_calls = -1;
         }
         if (h->host_pack) h->packer = new HostPacker(std::max(1, threads));
     }
-    if (h->host_pack) {
+    size_t total_points = 0;
+    for (int i = 0; i < count; ++i) total_points += scans[i].n_points;
+    const bool tuning = h->pack_tune_calls >= 0 && h->pack_tune_calls < 4 && h->packer && total_points > 0;
+    const bool use_pack = h->host_pack && h->packer && (!tuning || h->pack_tune_calls < 2);
+    const auto t_begin = std::chrono::steady_clock::now();
+    if (use_pack) {
         // Packed path: worker threads repack the clouds (14 useful bytes of every 32-byte record)
         // into pinned staging memory, group by group; as soon as a cloud is packed its H2D copy is
         // enqueued, and as soon as a stream group is complete its kernels are launched, so packing,
@@ -1056,7 +1109,14 @@ int gg_filter_cloud_batch(gg_handle h, int count, const gg_scan_desc* scans, con
             if (labels_out[i] && scans[i].n_points)
                 GG_CUDA(cudaMemcpyAsync(labels_out[i], h->view.labels + (size_t)scans[i].slot * h->pcap, scans[i].n_points, cudaMemcpyDeviceToHost,
                                         stream_of(h, scans[i].slot)));
-    return gg_synchronize(h);
+    rc = gg_synchronize(h);
+    if (tuning && rc == GG_OK) {
+        const double per_point = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count() / (double)total_points;
+        double& best = h->pack_best[use_pack ? 1 : 0];
+        best = std::min(best, per_point);
+        if (++h->pack_tune_calls == 4) h->host_pack = h->pack_best[1] < h->pack_best[0] ? 1 : 0;
+    }
+    return rc;
 }
 
 // Timing helpers: make every stream wait for the primary one / the primary one for all others,
@@ -1103,7 +1163,11 @@ int gg_host_pack_cloud(const gg_point* src, size_t n, unsigned char* dst) {
 }
 
 // number of host threads that repack clouds in gg_filter_cloud_batch (0: packing disabled or not used yet)
-int gg_host_pack_threads(gg_handle h) { return (h && h->host_pack && h->packer) ? h->packer->threads() + 1 : 0; }
+int gg_host_pack_threads(gg_handle h) {
+    if (!h || !h->host_pack || !h->packer) return 0;
+    if (h->pack_tune_calls >= 0 && h->pack_tune_calls < 4) return -(h->packer->threads() + 1);  // still measuring
+    return h->packer->threads() + 1;
+}
 
 int gg_get_layer(gg_handle h, int slot, const char* name, float* dst) {
     int rc = check_slot(h, slot);

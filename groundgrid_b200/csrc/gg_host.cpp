@@ -46,6 +46,7 @@ void derive_constants(const gg_config& c, double dimension_m, float resolution, 
     k.pc_var_thresh_f = (float)c.point_count_cell_variance_threshold;
     k.res_f = (float)res;
     k.res = res;
+    k.rres = 1.0 / res;
     k.len = (double)n * res;
     k.half = 0.5 * k.len;
     k.res_sq = (double)k.res_f * (double)k.res_f;
@@ -216,7 +217,7 @@ void build_spiral_skew(int n, const std::vector<int>& level_start, const std::ve
     t.levels = (int)level_start.size() - 1;
     if (K < 2) return;
     t.KP = ((K + 2 + 31) / 32) * 32;
-    if (4 * t.KP + 32 > 1024) return;  // one CTA: lane threads + the irregular warp
+    if (4 * t.KP > 4095) return;  // lane ids travel in 12 bits
     const size_t nv = visits.size();
     // level of the i-th visit of every cell (level order == visit order per cell)
     std::vector<std::vector<int>> cell_levels((size_t)n * n);
@@ -331,7 +332,7 @@ void build_spiral_skew(int n, const std::vector<int>& level_start, const std::ve
         const size_t cell = v.x + (size_t)v.y * n;
         int nb[9];
         bool regular = true;
-        uint32_t rec[4] = {0, 0, 0, 0};
+        uint32_t rec[4] = {0xffffu, 0xffffu, 0xffffu, 0xffffu};  // (q << 12) | producer lane, 0xffff = unused
         int nrec = 0;
         for (int q = 0; q < 9; ++q) {
             const int cx = v.x - 1 + q % 3, cy = v.y - 1 + q / 3;
@@ -347,7 +348,7 @@ void build_spiral_skew(int n, const std::vector<int>& level_start, const std::ve
             if (back < 1) return;  // contradicts the levelisation
             if (back == 1) {        // written one level ago: travels through shared memory
                 if (!(q == t.prev_q[v.s] && last_lane[ncell] == lane)) regular = false;
-                if (nrec < 4) rec[nrec] = 0x8000u | ((uint32_t)q << 10) | (uint32_t)last_lane[ncell];
+                if (nrec < 4) rec[nrec] = ((uint32_t)q << 12) | (uint32_t)last_lane[ncell];
                 ++nrec;
             }
         }

@@ -47,6 +47,7 @@ struct Const {
     float pc_var_thresh_f;  // (float) point_count_cell_variance_threshold (float >= int compare, :374)
     float res_f;            // (float) map.getResolution()
     double res;             // map.getResolution()  == (double) res_f
+    double rres;            // 1 / res (only to skip IEEE divisions whose integer part is not in doubt)
     double len, half;       // N * res, 0.5 * len
     double res_sq;          // res * res  (std::pow(resolution, 2.0), :332,356,463)
     double min_outlier_conf, outlier_tol;
@@ -77,9 +78,13 @@ struct SkewView {
     float* sd;              // [n_slots][slots] decayed confidence the visit will store, -1: confidence unchanged
     size_t slots;
     const int* cell_home;   // [N2][4]
-    const int* lane_begin;  // [lanes]
-    const int* lane_end;
-    const int* lane_cell0;  // [lanes] cell of the lane's first regular visit
+    // Lane threads are time-shared: ring k and ring k + M of one side are never active at the same
+    // level (ring k spans levels ~[3k, 5k]), so thread (side, m) walks rings m, m + M, m + 2M ... one
+    // after the other ("phases").  [phase][side * M + m] tables; an empty phase has begin == end.
+    const int* ph_begin;    // level range [begin, end) of the regular run
+    const int* ph_end;
+    const int* ph_cell0;    // cell (x + y * N) of the first regular visit
+    int M, phases;
     // irregular visits, one fixed-size block per level (irr_chunks x uint4):
     //   words [ (v * 9 + q) * 2 + {0, 1} ] = slot of neighbour q of visit v, producer lane if it was
     //                                        written one level ago (else 0xffffffff)
@@ -98,10 +103,8 @@ struct View {
     const float* expected;  // [N2] expectedPoints table (GroundSegmentation.cpp:40-46)
     gg_point* points;     // [n_slots][pcap]
     unsigned char* packed;  // [n_slots][14 * pcap] packed clouds (allocated on first use)
-    uint32_t* key;        // [n_slots][pcap] cell index of kept points, N2 for everything else
-    uint32_t* key2;       // sort ping-pong
-    float* zval;          // [n_slots][pcap] z per input point
-    float* z2;            // sort ping-pong
+    uint2* kz;            // [n_slots][pcap] (sort key, z bits) per input point: key = cell index of kept points, N2 for everything else
+    uint2* kz2;           // sort ping-pong (after the low-digit pass)
     float* zsorted;       // [n_slots][pcap] z of kept points grouped by cell, input order inside a cell
     float* dist;          // [n_slots][pcap] hypotf(x - ox, y - oy)
     uint32_t* code;       // [n_slots][pcap] class << 24 | cell

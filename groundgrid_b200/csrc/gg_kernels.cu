@@ -34,12 +34,22 @@ __device__ __forceinline__ int trunc_index(double v) {
     return __double2int_rz(v);
 }
 
+// trunc(a / res) exactly as the IEEE division would give it, without paying for the division in the
+// common case: q = a * (1 / res) differs from the correctly rounded quotient by a few ulp
+// (|q| < 1e6 here, so < 1e-9 absolute); whenever q is farther than 1e-6 from every integer, no
+// integer lies between the two values and trunc(q) == trunc(a / res).  Otherwise (a point within
+// a micro-cell of a cell boundary, or a huge / non-finite value) the real division decides.
+__device__ __forceinline__ int trunc_quotient(double a, double res, double rres) {
+    const double q = __dmul_rn(a, rres);
+    const double f = __dsub_rn(q, rint(q));
+    if (fabs(q) < 1.0e6 && fabs(f) > 1.0e-6) return __double2int_rz(q);
+    return trunc_index(__ddiv_rn(a, res));
+}
+
 // grid_map_core getIndexFromPosition with start index (0,0): -(int)((p - len/2 - pos) / res)
 __device__ __forceinline__ void grid_index(const Const& k, double px, double py, double x, double y, int& ix, int& iy) {
-    const double vx = __ddiv_rn(__dsub_rn(__dsub_rn(x, k.half), px), k.res);
-    const double vy = __ddiv_rn(__dsub_rn(__dsub_rn(y, k.half), py), k.res);
-    ix = -trunc_index(vx);
-    iy = -trunc_index(vy);
+    ix = -trunc_quotient(__dsub_rn(__dsub_rn(x, k.half), px), k.res, k.rres);
+    iy = -trunc_quotient(__dsub_rn(__dsub_rn(y, k.half), py), k.res, k.rres);
 }
 
 // grid_map_core checkIfPositionWithinMap: t = -(p - pos - len/2); 0 <= t < len
@@ -128,10 +138,6 @@ __device__ int block_exclusive_scan_1024(const int* in, int* out, int n) {
 // ------------------------------------------------------------------------------------------
 // fills / map init / roll
 // ------------------------------------------------------------------------------------------
-__global__ void k_fill(float* __restrict__ p, size_t n, float val) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = val;
-}
-
 // GroundGrid::update (GroundGrid.cpp:96-133,143): new(r, c) = old(r + shift_i, c + shift_j);
 // exposed cells: ground = -(T * (cx, cy, 0)).z in fp64, groundpatch = 0.
 __global__ void __launch_bounds__(256) k_roll_gather(View v, const SlotParams* __restrict__ batch) {
@@ -203,7 +209,6 @@ __device__ __forceinline__ uint32_t rasterize_point(const View& v, const SlotPar
     // std::pow(dx, 2.0) + std::pow(dy, 2.0) in double (:223); the same sum feeds hypotf (:170)
     const double sq = __dadd_rn(__dmul_rn((double)dxo, (double)dxo), __dmul_rn((double)dyo, (double)dyo));
     const float sqdist = (float)sq;
-    v.zval[base + i] = z;
     v.dist[base + i] = (float)__dsqrt_rn(sq);  // glibc hypotf: (float) sqrt((double)x*x + (double)y*y)
 
     uint32_t key = (uint32_t)k.N2;  // sentinel: not rasterised
@@ -263,7 +268,7 @@ __device__ __forceinline__ uint32_t rasterize_point(const View& v, const SlotPar
             }
         }
     }
-    v.key[base + i] = key;
+    v.kz[base + i] = make_uint2(key, __float_as_uint(z));  // one 8-byte element travels through the sort
     v.code[base + i] = code;
     return key;
 }
@@ -316,24 +321,26 @@ __global__ void __launch_bounds__(1024) k_sort_scan_hi(View v, const SlotParams*
 }
 
 // Stable scatter.  A block owns SORT_TILE consecutive items and walks them in rounds of
-// SORT_THREADS (thread order == item order).  Ranks inside a round come from
-// __match_any_sync (lanes of a warp) and a warp-ordered pass over the running per-digit
-// counters in shared memory, so equal digits keep their input order.
+// SORT_THREADS (thread order == item order).  Ranks inside a round: lanes of a warp rank
+// themselves with __match_any_sync, each (warp, digit) leader posts its count in a small
+// [warps][digits] table, and a thread's rank is the running digit count of earlier rounds + the
+// counts of earlier warps + its rank inside the warp -- two barriers per round, equal digits keep
+// their input order.
 template <bool LAST>
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(View v, const SlotParams* __restrict__ batch, const uint32_t* __restrict__ keys_in,
-                                                               const float* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
-                                                               float* __restrict__ vals_out, int shift, int bits, int nb) {
-    extern __shared__ int s_run[];
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(View v, const SlotParams* __restrict__ batch, const uint2* __restrict__ kz_in,
+                                                               uint2* __restrict__ kz_out, float* __restrict__ vals_out, int shift, int bits, int nb) {
+    extern __shared__ int s_run[];  // [D] running per-digit count, then [WARPS][D] u16 counts of the current round
     constexpr int ROUNDS = SORT_TILE / SORT_THREADS;
     constexpr int WARPS = SORT_THREADS / 32;
     const SlotParams& sp = batch[blockIdx.y];
     const int D = 1 << bits;
+    unsigned short* s_wc = reinterpret_cast<unsigned short*>(s_run + D);
     for (int d = threadIdx.x; d < D; d += SORT_THREADS) s_run[d] = 0;
+    for (int d = threadIdx.x; d < WARPS * D / 2; d += SORT_THREADS) reinterpret_cast<int*>(s_wc)[d] = 0;
     __syncthreads();
     const int n = sp.n_points;
     const size_t base = (size_t)sp.slot * v.pcap;
-    const uint32_t* kin = keys_in + base;
-    const float* vin = vals_in + base;
+    const uint2* kin = kz_in + base;
     const int tile0 = blockIdx.x * SORT_TILE;
     const uint32_t mask = (uint32_t)D - 1u;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -346,8 +353,9 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(View v, const Slo
     for (int r = 0; r < ROUNDS; ++r) {
         const int idx = tile0 + r * SORT_THREADS + threadIdx.x;
         const bool valid = idx < n;
-        my_key[r] = valid ? kin[idx] : 0u;
-        my_val[r] = valid ? vin[idx] : 0.0f;
+        const uint2 e = valid ? kin[idx] : make_uint2(0u, 0u);
+        my_key[r] = e.x;
+        my_val[r] = __uint_as_float(e.y);
     }
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
@@ -357,32 +365,45 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(View v, const Slo
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
         const int rank_in_warp = __popc(peers & lt_mask);
         const int total = __popc(peers);
-        int basecnt = 0;
-        for (int w = 0; w < WARPS; ++w) {
-            if (warp == w) {
-                if (valid) basecnt = s_run[d];
-                __syncwarp();
-                if (valid && rank_in_warp == 0) s_run[d] = basecnt + total;
-            }
-            __syncthreads();
+        const bool leader = valid && rank_in_warp == 0;
+        if (leader) s_wc[warp * D + d] = (unsigned short)total;
+        __syncthreads();
+        int before = 0;
+        if (valid) {
+            before = s_run[d];
+            for (int w = 0; w < warp; ++w) before += s_wc[w * D + d];
         }
-        my_rank[r] = basecnt + rank_in_warp;
+        my_rank[r] = before + rank_in_warp;
+        __syncthreads();
+        if (leader) {
+            atomicAdd(&s_run[d], total);
+            s_wc[warp * D + d] = 0;
+        }
+        __syncwarp();
     }
     const size_t hoff = (size_t)sp.slot * ((size_t)v.sort_blocks << max(v.bits_lo, v.bits_hi));
-    const int* offs = (LAST ? v.sort_hist2 : v.sort_hist) + hoff;
+    const int* __restrict__ offs = (LAST ? v.sort_hist2 : v.sort_hist) + hoff;
     int* hist2 = v.sort_hist2 + hoff;
+    // fetch all tile offsets first (read-only path: the table is not written by this kernel), so that
+    // the eight L2 latencies overlap instead of serialising behind the stores / atomics below
+    int my_off[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int idx = tile0 + r * SORT_THREADS + threadIdx.x;
+        my_off[r] = idx < n ? __ldg(offs + (int)((my_key[r] >> shift) & mask) * nb + blockIdx.x) : 0;
+    }
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) {
         const int idx = tile0 + r * SORT_THREADS + threadIdx.x;
         if (idx < n) {
-            const int d = (int)((my_key[r] >> shift) & mask);
-            const int pos = offs[d * nb + blockIdx.x] + my_rank[r];
+            const int pos = my_off[r] + my_rank[r];
             if (!LAST) {
-                keys_out[base + pos] = my_key[r];
+                kz_out[base + pos] = make_uint2(my_key[r], __float_as_uint(my_val[r]));
                 // histogram of the next pass: high digit x destination tile
                 atomicAdd(&hist2[(int)(my_key[r] >> bits) * nb + pos / SORT_TILE], 1);
+            } else {
+                vals_out[base + pos] = my_val[r];
             }
-            vals_out[base + pos] = my_val[r];
         }
     }
 }
@@ -395,8 +416,13 @@ template <bool FULL>
 __global__ void __launch_bounds__(128) k_cell_stats(View v, const SlotParams* __restrict__ batch) {
     const SlotParams& sp = batch[blockIdx.y];
     const Const& k = v.k;
-    const int cell = blockIdx.x * 128 + threadIdx.x;
-    if (cell >= k.N2) return;
+    // a warp owns an 8 x 4 patch of cells: point density varies with the distance to the sensor, so a
+    // compact patch has far more uniform per-cell counts (= loop trip counts) than a 32 x 1 strip
+    const int wid = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int tiles_i = (k.N + 7) >> 3;
+    const int ci = (wid % tiles_i) * 8 + (lane & 7), cj = (wid / tiles_i) * 4 + (lane >> 3);
+    if (ci >= k.N || cj >= k.N) return;
+    const int cell = ci + cj * k.N;
     const size_t coff = (size_t)sp.slot * k.N2;
     const int cnt = v.cnt_i[coff + cell];
     const float* zs = v.zsorted + (size_t)sp.slot * v.pcap + v.cellstart[coff + cell];
@@ -819,20 +845,52 @@ template <int SIDE>
 __device__ __forceinline__ void skew_lane_thread(const View& v, const SlotParams& sp, float2* s_xch) {
     const SkewView& w = v.skew;
     constexpr int PQ = SIDE == 0 ? 1 : (SIDE == 1 ? 3 : (SIDE == 2 ? 7 : 5));  // neighbour index of the lane's previous cell
-    const int tid = threadIdx.x;
-    const int L = w.levels, KP = w.KP, lanes = w.lanes;
+    constexpr int PF_FAR = 8, PF_NEAR = 2;
+    const int L = w.levels, KP = w.KP, lanes = w.lanes, M = w.M;
+    const int m = threadIdx.x - SIDE * M;  // this thread walks rings m - 1, m - 1 + M, m - 1 + 2M, ... of side SIDE
     float2* __restrict__ SK = w.sk + (size_t)sp.slot * w.slots;
     const float* __restrict__ SD = w.sd + (size_t)sp.slot * w.slots;
-    const int lb = w.lane_begin[tid], le = w.lane_end[tid];
     float* __restrict__ Gn = v.layer(sp.slot, L_GROUND);
     float* __restrict__ Cn = v.layer(sp.slot, L_GROUNDPATCH);
     const int cstep = SIDE == 0 ? v.k.N : (SIDE == 1 ? 1 : (SIDE == 2 ? -v.k.N : -1));  // the lane walks +y, +x, -y, -x
-    const int cell0 = w.lane_cell0[tid] - lb * cstep;                                      // cell of level l: cell0 + l * cstep
     int off[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) off[q] = w.pattern[SIDE * 9 + q];
-    // slot of this lane at level l: base0 + l * KP
-    const int base0 = (SIDE * w.rows + w.row0) * KP + (tid - SIDE * KP);
+    // The only slot a regular visit touches for the first time (i.e. that still sits in HBM / L2) is
+    // the newest row of its outer ring, plus its SD entry; everything else was read by this SM a
+    // few levels ago.  Those two are prefetched PF_FAR levels ahead into L2 and PF_NEAR levels ahead
+    // into L1, so the one-level-ahead loads below are cache hits.
+    int off_new = off[0];
+#pragma unroll
+    for (int q = 1; q < 9; ++q) off_new = max(off_new, off[q]);
+
+    // current phase: level range [lb, le) of the regular run, slot of level l = base0 + l * KP,
+    // cell of level l = cell0 + l * cstep, exchange-buffer index xid
+    int ph = -1, lb = 0, le = 0, base0 = 0, cell0 = 0, xid = 0;
+    int w_first = 0, w_last = 0;  // levels in which any lane of this warp has work (or prefetches)
+    auto next_phase = [&]() {
+        ++ph;
+        const size_t e = ((size_t)ph * 4 + SIDE) * M + m;
+        const int col = ph * M + m;
+        lb = w.ph_begin[e];
+        le = w.ph_end[e];
+        base0 = (SIDE * w.rows + w.row0) * KP + col;
+        cell0 = w.ph_cell0[e] - lb * cstep;
+        xid = SIDE * KP + col;
+    };
+    auto warp_window = [&]() {
+        w_first = lb < le ? lb - PF_FAR : 0x7fffffff;
+        w_last = lb < le ? le : -1;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            w_first = min(w_first, __shfl_xor_sync(0xffffffffu, w_first, d));
+            w_last = max(w_last, __shfl_xor_sync(0xffffffffu, w_last, d));
+        }
+        w_first = max(w_first, 0) & ~1;  // iterations cover two levels
+    };
+    next_phase();
+    warp_window();
+
     float2 A[9], B[9];
     float dA = -1.0f, dB = -1.0f;
 #pragma unroll
@@ -842,14 +900,6 @@ __device__ __forceinline__ void skew_lane_thread(const View& v, const SlotParams
         for (int q = 0; q < 9; ++q) A[q] = SK[base0 + off[q]];
         dA = SD[base0];
     }
-    // The only slot a regular visit touches for the first time (i.e. that still sits in HBM / L2) is
-    // the newest row of its outer ring, plus its SD entry; everything else was read by this SM a
-    // few levels ago.  Those two are prefetched PF_FAR levels ahead into L2 and PF_NEAR levels ahead
-    // into L1, so the one-level-ahead loads below are cache hits.
-    int off_new = off[0];
-#pragma unroll
-    for (int q = 1; q < 9; ++q) off_new = max(off_new, off[q]);
-    constexpr int PF_FAR = 8, PF_NEAR = 2;
     // two levels per iteration, alternating register sets (a copy would wait for the loads)
 #define GG_LANE_LEVEL(l_, CUR, CURD, NXT, NXTD)                                                      \
     {                                                                                               \
@@ -868,25 +918,27 @@ __device__ __forceinline__ void skew_lane_thread(const View& v, const SlotParams
             NXTD = SD[base0 + (l__ + 1) * KP];                                                      \
         }                                                                                           \
         if (l__ >= lb && l__ < le) {                                                                \
-            CUR[PQ] = s_xch[((l__ + 1) & 1) * lanes + tid];                                         \
+            CUR[PQ] = s_xch[((l__ + 1) & 1) * lanes + xid];                                         \
             const float2 r__ = spiral_visit(CUR, CURD);                                             \
-            s_xch[(l__ & 1) * lanes + tid] = r__;                                                   \
+            s_xch[(l__ & 1) * lanes + xid] = r__;                                                   \
             SK[base0 + l__ * KP] = r__;                                                             \
             Gn[cell0 + l__ * cstep] = r__.x;                                                        \
             if (CURD >= 0.0f) Cn[cell0 + l__ * cstep] = r__.y;                                      \
         }                                                                                           \
         __syncthreads();                                                                            \
     }
-    // a warp (32 consecutive rings of one side) has work only in a window of levels; outside of it
-    // the per-level cost must be the barrier alone (the level time is set by instruction issue)
-    int w_first = lb < le ? lb - PF_FAR : 0x7fffffff, w_last = lb < le ? le : -1;
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        w_first = min(w_first, __shfl_xor_sync(0xffffffffu, w_first, d));
-        w_last = max(w_last, __shfl_xor_sync(0xffffffffu, w_last, d));
-    }
-    w_first = max(w_first, 0) & ~1;  // iterations cover two levels
     for (int l = 0; l < L; l += 2) {
+        // done with this ring: move on to ring + M (it starts well after this one ended)
+        if (w.phases > 1) {
+            bool moved = false;
+            while (ph + 1 < w.phases && l >= le) {
+                next_phase();
+                moved = true;
+            }
+            if (__any_sync(0xffffffffu, moved)) warp_window();
+        }
+        // a warp (32 consecutive rings of one side) has work only in a window of levels; outside of it
+        // the per-level cost must be the barrier alone (the level time is set by instruction issue)
         if (l < w_first || l >= w_last) {
             __syncthreads();
             if (l + 1 < L) __syncthreads();
@@ -902,7 +954,7 @@ __device__ __forceinline__ void skew_named_barrier() { asm volatile("bar.sync 1,
 
 __device__ __forceinline__ void skew_irregular_thread(const View& v, const SlotParams& sp, float2* s_xch, uint4* s_ring, float2* s_nb, float* s_dd) {
     const SkewView& w = v.skew;
-    const int ti = threadIdx.x - w.lanes;  // 0 .. 63
+    const int ti = threadIdx.x - 4 * w.M;  // 0 .. 63
     const int L = w.levels, lanes = w.lanes;
     const int chunks = w.irr_chunks, irr_max = w.irr_max;
     float2* __restrict__ SK = w.sk + (size_t)sp.slot * w.slots;
@@ -1006,8 +1058,8 @@ __global__ void __launch_bounds__(MAXT) k_spiral_skew(View v, const SlotParams* 
     float* s_dd = reinterpret_cast<float*>(s_nb + w.irr_max * 9);
     const SlotParams& sp = batch[blockIdx.x];
     const int tid = threadIdx.x;
-    if (tid < w.lanes) {
-        const int side = tid / w.KP;  // warp-uniform: KP is a multiple of 32
+    if (tid < 4 * w.M) {
+        const int side = tid / w.M;  // warp-uniform: M is a multiple of 32
         if (side == 0)
             skew_lane_thread<0>(v, sp, s_xch);
         else if (side == 1)
@@ -1040,7 +1092,7 @@ __global__ void __launch_bounds__(256) k_label(View v, const SlotParams* __restr
         const double groundheight = (double)v.layer(sp.slot, L_GROUND)[cell];
         const float variance = v.layer(sp.slot, L_VARIANCE)[cell];
         const float dist = v.dist[base + i];
-        const float z = v.zval[base + i];
+        const float z = __uint_as_float(v.kz[base + i].y);
         // std::max(std::min((f * dist) / variance * thres, thres), obs_thres) with C++ min/max semantics
         const double a = __dmul_rn(__ddiv_rn(__dmul_rn(k.lab_fac, (double)dist), (double)variance), k.lab_thres);
         double t = (k.lab_thres < a) ? k.lab_thres : a;
@@ -1201,22 +1253,30 @@ __global__ void __launch_bounds__(256) k_eval_counts(View v, const SlotParams* _
 // ------------------------------------------------------------------------------------------
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
-int launch_init_map(const View& v, int slot, float z, cudaStream_t st) {
-    const size_t n = (size_t)v.k.N2;
-    const int blocks = (int)((n + 255) / 256);
-    k_fill<<<blocks, 256, 0, st>>>(v.layer(slot, L_GROUND), n, z);
-    k_fill<<<blocks, 256, 0, st>>>(v.layer(slot, L_GROUNDPATCH), n, (float)0.0000001);
-    k_fill<<<blocks, 256, 0, st>>>(v.layer(slot, L_OBSTACLES), n, 0.0f);
-    k_fill<<<blocks, 256, 0, st>>>(v.layer(slot, L_COUNT), n, 0.0f);
-    k_fill<<<blocks, 256, 0, st>>>(v.layer(slot, L_VARIANCE), n, 0.0f);
-    k_fill<<<blocks, 256, 0, st>>>(v.layer(slot, L_MINH), n, 100.0f);
-    int launches = 6;
+// GroundGrid::initGroundGrid (src/GroundGrid.cpp:71-75): ground = z, groundpatch = 1e-7, points = 0,
+// min = 100, max = -100; the per-scan layers start at 0.
+__global__ void __launch_bounds__(256) k_init_map(View v, int slot, float z) {
+    const int cell = blockIdx.x * 256 + threadIdx.x;
+    if (cell >= v.k.N2) return;
+    v.layer(slot, L_GROUND)[cell] = z;
+    v.layer(slot, L_GROUNDPATCH)[cell] = (float)0.0000001;
+    v.layer(slot, L_OBSTACLES)[cell] = 0.0f;
+    v.layer(slot, L_COUNT)[cell] = 0.0f;
+    v.layer(slot, L_VARIANCE)[cell] = 0.0f;
+    v.layer(slot, L_MINH)[cell] = 100.0f;
     if (v.k.full_layers) {
-        k_fill<<<blocks, 256, 0, st>>>(v.layer(slot, L_MAXH), n, -100.0f);
-        for (int l : {L_GCAND, L_PLANEDIST, L_M2, L_MEAN, L_RAW}) k_fill<<<blocks, 256, 0, st>>>(v.layer(slot, l), n, 0.0f);
-        launches += 6;
+        v.layer(slot, L_MAXH)[cell] = -100.0f;
+        v.layer(slot, L_GCAND)[cell] = 0.0f;
+        v.layer(slot, L_PLANEDIST)[cell] = 0.0f;
+        v.layer(slot, L_M2)[cell] = 0.0f;
+        v.layer(slot, L_MEAN)[cell] = 0.0f;
+        v.layer(slot, L_RAW)[cell] = 0.0f;
     }
-    return launches;
+}
+
+int launch_init_map(const View& v, int slot, float z, cudaStream_t st) {
+    k_init_map<<<cdiv(v.k.N2, 256), 256, 0, st>>>(v, slot, z);
+    return 1;
 }
 
 struct Mark {
@@ -1254,19 +1314,19 @@ int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int 
     size_t sh = sizeof(int) << v.bits_lo;
     GG_LAUNCH(K_RASTERIZE, k_rasterize<<<dim3(nb, count), SORT_THREADS, sh, st>>>(v, batch, nb));
     GG_LAUNCH(K_SCAN_LO_CELLS, k_scan_lo_cells<<<2 * count, 1024, 0, st>>>(v, batch, count, nb));
-    GG_LAUNCH(K_SORT_SCATTER1,
-              k_sort_scatter<false><<<dim3(nb, count), SORT_THREADS, sh, st>>>(v, batch, v.key, v.zval, v.key2, v.z2, 0, v.bits_lo, nb));
+    GG_LAUNCH(K_SORT_SCATTER1, k_sort_scatter<false><<<dim3(nb, count), SORT_THREADS, sh + ((size_t)(SORT_THREADS / 32) * 2 << v.bits_lo), st>>>(
+                                   v, batch, v.kz, v.kz2, nullptr, 0, v.bits_lo, nb));
     // pass 2 (high digit): its histogram was accumulated by the pass-1 scatter; (key2, z2) -> zsorted
     sh = sizeof(int) << v.bits_hi;
     GG_LAUNCH(K_SORT_SCAN2, k_sort_scan_hi<<<count, 1024, 0, st>>>(v, batch, nb));
-    GG_LAUNCH(K_SORT_SCATTER2, k_sort_scatter<true><<<dim3(nb, count), SORT_THREADS, sh, st>>>(v, batch, v.key2, v.z2, nullptr, v.zsorted,
-                                                                                             v.bits_lo, v.bits_hi, nb));
+    GG_LAUNCH(K_SORT_SCATTER2, k_sort_scatter<true><<<dim3(nb, count), SORT_THREADS, sh + ((size_t)(SORT_THREADS / 32) * 2 << v.bits_hi), st>>>(
+                                   v, batch, v.kz2, nullptr, v.zsorted, v.bits_lo, v.bits_hi, nb));
     launches += 5;
 
     if (v.k.full_layers)
-        GG_LAUNCH(K_CELL_STATS, k_cell_stats<true><<<dim3(cdiv(N2, 128), count), 128, 0, st>>>(v, batch));
+        GG_LAUNCH(K_CELL_STATS, k_cell_stats<true><<<dim3(cdiv(cdiv(v.k.N, 8) * cdiv(v.k.N, 4), 4), count), 128, 0, st>>>(v, batch));
     else
-        GG_LAUNCH(K_CELL_STATS, k_cell_stats<false><<<dim3(cdiv(N2, 128), count), 128, 0, st>>>(v, batch));
+        GG_LAUNCH(K_CELL_STATS, k_cell_stats<false><<<dim3(cdiv(cdiv(v.k.N, 8) * cdiv(v.k.N, 4), 4), count), 128, 0, st>>>(v, batch));
     ++launches;
     if (stop_after == 1) return launches;
 
@@ -1275,7 +1335,7 @@ int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int 
     if (stop_after == 2) return launches;
 
     if (v.skew.sk) {
-        const int threads = v.skew.lanes + SKEW_IRR_THREADS;
+        const int threads = 4 * v.skew.M + SKEW_IRR_THREADS;
         const size_t shm = (size_t)SKEW_RING * v.skew.irr_chunks * sizeof(uint4) + (size_t)2 * v.skew.lanes * sizeof(float2) +
                            (size_t)v.skew.irr_max * 9 * sizeof(float2) + (size_t)v.skew.irr_max * sizeof(float) + 16;
         if (threads <= 768)

@@ -285,7 +285,7 @@ def host_spiral_skew(n):
                 home=home.reshape(n * n, 4), irr_level_start=ils, irr=recs.reshape(-1, 16))
 
 
-@pytest.mark.parametrize("dim,res", [(13.2, 0.33), (33.0, 0.33), (99.0, 0.33), (120.0, 0.33)])
+@pytest.mark.parametrize("dim,res", [(13.2, 0.33), (33.0, 0.33), (99.0, 0.33), (120.0, 0.33), (120.0, 0.2)])
 def test_skewed_spiral_tables_emulation(dim, res):
     """CPU emulation of k_skew -> k_spiral_skew -> k_unskew: lane threads follow the fixed offset
     pattern in (level, ring) space, the irregular warp follows explicit records, neighbourhoods are
@@ -372,9 +372,9 @@ def test_skewed_spiral_tables_emulation(dim, res):
         for w in (10, 11):
             for sh in (0, 16):
                 e = (r[:, w] >> sh) & 0xFFFF
-                m = (e & 0x8000) != 0
-                q = ((e >> 10) & 15).astype(np.int64)
-                pl = (e & 1023).astype(np.int64)
+                m = e != 0xFFFF
+                q = np.where(m, e >> 12, 0).astype(np.int64)
+                pl = (e & 4095).astype(np.int64)
                 igg[m, q[m]] = xg[pb, pl[m]]
                 icc[m, q[m]] = xc[pb, pl[m]]
         ing, inc = visit(igg, icc, idd)
