@@ -123,6 +123,10 @@ class ClockSampler:
                 "power_w_max": float(max(power))}
 
 
+def P_mean_single(npts):
+    return float(npts[0].mean())
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -380,6 +384,32 @@ def main():
                "host_pack_threads": max(0, g.host_pack_threads),
                "pcie_bytes_per_point": 14 if g.host_pack_threads > 0 else 32}
 
+    # ---- latency of ONE stream (configs[1] read literally: scan t+1 needs the prior of scan t)
+    single = None
+    if rank == 0:
+        d1 = [g.make_descs([0], [int(npts[0, s])], [streams[0][s][1]], [0.0]) for s in range(S)]
+        p1 = [[dev_pool.data_ptr() + int(offs[0, s])] for s in range(S)]
+        sl = np.array([0], np.int32)
+
+        def one_scan(t):
+            s = pingpong(t, S)
+            g.update_pose_batch(sl, xy[s][:1], Ts[s][:1])
+            g.run_scans_device(d1[s], p1[s])
+
+        for t in range(5):
+            one_scan(tstep[0] + t)
+        g.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(ext)
+        n_single = 50
+        for t in range(n_single):
+            one_scan(tstep[0] + 5 + t)
+        a1.record(ext)
+        g.synchronize()
+        ms = a0.elapsed_time(a1) / n_single
+        single = {"ms_per_scan": ms, "scans_per_s": 1e3 / ms, "value": P_mean_single(npts) / ms / 1e3, "unit": UNIT,
+                  "note": "one stream, scans strictly in sequence (update + filter_cloud per scan), clouds resident in HBM"}
+
     # ---- roofline of the dominant kernel (CUDA events around every launch, same timed region)
     P_mean = float(npts.mean())
     N2 = float(N_CELLS * N_CELLS)
@@ -394,10 +424,17 @@ def main():
     roofline = None
     if dom:
         dom_ms, dom_n = prof[dom]
-        per_launch_bytes = algorithmic_bytes(dom, P_mean, N2) * B
+        scans_per_launch = B / max(1, g.n_streams)          # one launch covers the scans of one stream group
+        per_launch_bytes = algorithmic_bytes(dom, P_mean, N2) * scans_per_launch
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):                            # DRAM bytes of that kernel from the committed ncu capture
+            per_scan = json.load(open(tpath))["bytes_per_scan"].get(dom)
+            traffic = per_scan * scans_per_launch if per_scan else None
         achieved = per_launch_bytes / (dom_ms / dom_n * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "avg_launch_us": dom_ms / dom_n * 1e3,
+                    "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu --set full, scaled to the scans of one launch)",
+                    "peak_source": peak_src, "scans_per_launch": scans_per_launch, "avg_launch_us": dom_ms / dom_n * 1e3,
                     "algorithmic_bytes_per_launch": per_launch_bytes, "kernel_time_shares": shares,
                     "kernel_avg_launch_us": {k: round(v[0] / v[1] * 1e3, 1) for k, v in prof.items()}}
     path_bytes = (45.0 * P_mean + 72.0 * N2 + 16.0 * N2) * B     # + roll every step
@@ -439,7 +476,7 @@ def main():
                        "l2": f"inputs larger than L2: {B * P_mean * 32 / 1e6:.0f} MB of clouds + {B * 6 * N2 * 4 / 1e6:.0f} MB of layers per step vs 126 MB L2",
                        "layers": "live layers only (dead layers of SURVEY f2 off)", "cuda_streams": g.n_streams},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_path": roofline_path,
-            "cpu_baseline": cpu, "scans_per_s": value * 1e6 / P_mean,
+            "cpu_baseline": cpu, "scans_per_s": value * 1e6 / P_mean, "single_stream": single,
         }
         print(json.dumps(line), flush=True)
     barrier()
