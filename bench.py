@@ -229,6 +229,27 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """numactl --cpunodebind equivalent: keep this rank (and the pinned host buffers it allocates next) on
+    the CPUs of the socket its GPU hangs off.  Returns a description for the JSON line."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "unchanged"
+        os.sched_setaffinity(0, cpus)
+        return "cpus %s (NUMA node of GPU %s)" % (text, bdf)
+    except (OSError, ValueError, AttributeError):
+        return "unchanged"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -240,6 +261,7 @@ def main():
     ap.add_argument("--cpu-scans", type=int, default=300, help="scans of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-bind", action="store_true", help="do not bind the process to the NUMA node of its GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -264,6 +286,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: groundgrid_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    affinity = "unchanged" if args.no_bind else bind_to_gpu_numa_node(torch, local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -283,7 +306,7 @@ def main():
             raw = np.ascontiguousarray(streams[b][s][0]).view(np.uint8).reshape(-1)
             hp[offs[b, s]:offs[b, s] + raw.size] = raw
     dev_pool = host_pool.cuda()
-    host_labels = torch.zeros((B, PCAP), dtype=torch.uint8).pin_memory()
+    host_labels = torch.zeros((2, B, PCAP), dtype=torch.uint8).pin_memory()   # two sets: batches overlap in the e2e loop
 
     g = capi.GroundGridB200(DIM_M, RES, device=local_rank, n_slots=B, max_points=PCAP, full_layers=False)
     for b in range(B):
@@ -296,7 +319,7 @@ def main():
         host_ptrs.append([host_pool.data_ptr() + int(offs[b, s]) for b in range(B)])
         xy.append(np.tile(np.array([float(s), 0.0]), (B, 1)))
         Ts.append(np.tile(synth.base_from_map(float(s), 0.0).reshape(1, 12), (B, 1)))
-    lab_ptrs = [host_labels.data_ptr() + b * PCAP for b in range(B)]
+    lab_ptrs = [[host_labels.data_ptr() + (q * B + b) * PCAP for b in range(B)] for q in range(2)]
     pts_per_pose = npts.sum(axis=0)
 
     ext = torch.cuda.ExternalStream(g.stream, device=local_rank)
@@ -310,13 +333,32 @@ def main():
         tstep[0] += 1
         return s
 
-    def step_e2e():
+    in_flight = [None]
+    last_label_set = [0]
+
+    def step_e2e(overlap=True):
+        """One scan of every stream through the host-buffer call.  overlap: the call is issued in its two halves
+        (gg_filter_cloud_batch_begin / _wait), so the clouds of this step cross the bus while the kernels of the
+        previous step finish; its labels are complete one step later."""
         s = pingpong(tstep[0], S)
         if tstep[0]:
             g.update_pose_batch(slots, xy[s], Ts[s])
-        g.filter_cloud_batch_ptrs(descs[s], host_ptrs[s], lab_ptrs)
+        q = tstep[0] & 1
+        if overlap:
+            ticket = g.filter_cloud_batch_begin(descs[s], host_ptrs[s], lab_ptrs[q])
+            if in_flight[0] is not None:
+                g.filter_cloud_batch_wait(in_flight[0])
+            in_flight[0] = ticket
+        else:
+            g.filter_cloud_batch_ptrs(descs[s], host_ptrs[s], lab_ptrs[q])
+        last_label_set[0] = q
         tstep[0] += 1
         return s
+
+    def drain_e2e():
+        if in_flight[0] is not None:
+            g.filter_cloud_batch_wait(in_flight[0])
+            in_flight[0] = None
 
     def barrier():
         g.synchronize()
@@ -366,23 +408,49 @@ def main():
     # ---- end to end through the host-buffer C-ABI call
     e2e = None
     if not args.no_e2e:
-        for _ in range(6):     # also lets the library settle on packed vs plain H2D (it measures both, twice each)
+        for _ in range(max(3, args.warmup)):
+            step_e2e(overlap=False)
+        barrier()
+        n_sync = max(3, args.steps // 2)          # the plain synchronous call, for comparison
+        t0 = time.perf_counter()
+        pts_sync = 0
+        tail_us = 0
+        for _ in range(n_sync):
+            pts_sync += int(pts_per_pose[step_e2e(overlap=False)])
+            tr = g.last_batch_transfer()
+            tail_us += tr[5] - tr[4]
+        barrier()
+        dt_sync = max_over_ranks(time.perf_counter() - t0)
+        for _ in range(2):
             step_e2e()
+        drain_e2e()
         barrier()
         t0 = time.perf_counter()
         pts_e2e = 0
         h2d = 0
+        n_packed = n_raw = 0
+        feed_us = 0
         for _ in range(args.steps):
             s = step_e2e()
             pts_e2e += int(pts_per_pose[s])
-            h2d = int(pts_per_pose[s]) * (14 if g.host_pack_threads > 0 else 32)
+            tr = g.last_batch_transfer()
+            n_packed += tr[0]
+            n_raw += tr[1]
+            h2d += tr[2] + tr[3]
+            feed_us += tr[4]
+        drain_e2e()
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": sum_over_ranks(pts_e2e) / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(h2d)),
+        e2e = {"value": sum_over_ranks(pts_e2e) / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(h2d) / args.steps),
                "d2h_bytes_per_step": int(sum_over_ranks(int(pts_per_pose.max()))), "ms_per_step": dt / args.steps * 1e3,
-               "api": "gg_update_pose_batch + gg_filter_cloud_batch (pinned host PointXYZIR clouds in, labels out)",
+               "api": "gg_update_pose_batch + gg_filter_cloud_batch_begin/_wait (pinned host PointXYZIR clouds in, labels out; "
+                      "the H2D of step t+1 overlaps the kernels and the label read-back of step t)",
+               "synchronous_call": {"value": sum_over_ranks(pts_sync) / dt_sync / 1e6, "unit": UNIT, "ms_per_step": dt_sync / n_sync * 1e3,
+                                    "ms_after_last_cloud_enqueued": tail_us / n_sync / 1e3, "api": "gg_filter_cloud_batch"},
                "host_pack_threads": max(0, g.host_pack_threads),
-               "pcie_bytes_per_point": 14 if g.host_pack_threads > 0 else 32}
+               "begin_call_ms": feed_us / args.steps / 1e3,
+               "scans_repacked_14B": n_packed, "scans_raw_32B": n_raw,
+               "pcie_bytes_per_point": round(h2d / max(1, pts_e2e), 2)}
 
     # ---- latency of ONE stream (configs[1] read literally: scan t+1 needs the prior of scan t)
     single = None
@@ -455,7 +523,7 @@ def main():
         match = None
         if n_chk == t_done and t_done:
             s_last = pingpong(t_done - 1, S)
-            match = bool(np.array_equal(host_labels[0, :int(npts[0, s_last])].numpy(), labs[t_done - 1])) if not args.no_e2e else None
+            match = bool(np.array_equal(host_labels[last_label_set[0], 0, :int(npts[0, s_last])].numpy(), labs[t_done - 1])) if not args.no_e2e else None
         best, cores = (v1, 1) if v1 >= v8 else (v8, 8)
         cpu = {"value": best, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"stream 0, {n_cpu} consecutive scans (update + filter_cloud), oracle port of the reference; "
@@ -474,7 +542,8 @@ def main():
                        "streams_per_gpu": B, "poses_per_stream": S, "points_per_scan_mean": P_mean, "cells": N_CELLS,
                        "parallelism": f"scans sharded one-stream-set-per-GPU x{world}, no data-path collective",
                        "l2": f"inputs larger than L2: {B * P_mean * 32 / 1e6:.0f} MB of clouds + {B * 6 * N2 * 4 / 1e6:.0f} MB of layers per step vs 126 MB L2",
-                       "layers": "live layers only (dead layers of SURVEY f2 off)", "cuda_streams": g.n_streams},
+                       "layers": "live layers only (dead layers of SURVEY f2 off)", "cuda_streams": g.n_streams,
+                       "host_affinity": affinity},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_path": roofline_path,
             "cpu_baseline": cpu, "scans_per_s": value * 1e6 / P_mean, "single_stream": single,
         }

@@ -88,6 +88,8 @@ def load(build_if_missing=True):
         "gg_set_map_position": (i, [vp, i, d, d]),
         "gg_filter_cloud": (i, [vp, i, vp, sz, vp, d, vp, vp, vp, C.POINTER(sz)]),
         "gg_filter_cloud_batch": (i, [vp, i, vp, vp, vp]),
+        "gg_filter_cloud_batch_begin": (i, [vp, i, vp, vp, vp, C.POINTER(i)]),
+        "gg_filter_cloud_batch_wait": (i, [vp, i]),
         "gg_upload_points": (i, [vp, i, vp, sz]),
         "gg_run_scans": (i, [vp, i, vp, i]),
         "gg_download_labels": (i, [vp, i, vp, sz]),
@@ -108,6 +110,7 @@ def load(build_if_missing=True):
         "gg_stream": (vp, [vp]),
         "gg_num_streams": (i, [vp]),
         "gg_host_pack_threads": (i, [vp]),
+        "gg_last_batch_transfer": (i, [vp, C.POINTER(C.c_size_t)]),
         "gg_fork_streams": (i, [vp]),
         "gg_join_streams": (i, [vp]),
         "gg_kernel_launches": (C.c_uint64, [vp]),
@@ -254,6 +257,12 @@ class GroundGridB200:
     def host_pack_threads(self):
         return self._l.gg_host_pack_threads(self._h)
 
+    def last_batch_transfer(self):
+        """(scans packed, scans raw, packed H2D bytes, raw H2D bytes, feed us, total us) of the last batch call."""
+        info = (C.c_size_t * 6)()
+        _check(self._l.gg_last_batch_transfer(self._h, info))
+        return tuple(int(v) for v in info)
+
     def fork_streams(self):
         _check(self._l.gg_fork_streams(self._h))
 
@@ -359,6 +368,18 @@ class GroundGridB200:
         pp = (C.c_void_p * n)(*point_ptrs)
         lp = (C.c_void_p * n)(*label_ptrs) if label_ptrs is not None else None
         _check(self._l.gg_filter_cloud_batch(self._h, n, descs, pp, lp))
+
+    def filter_cloud_batch_begin(self, descs, point_ptrs, label_ptrs):
+        """First half of filter_cloud_batch_ptrs: returns a ticket once everything is enqueued."""
+        n = len(descs)
+        pp = (C.c_void_p * n)(*point_ptrs)
+        lp = (C.c_void_p * n)(*label_ptrs) if label_ptrs is not None else None
+        ticket = C.c_int(-1)
+        _check(self._l.gg_filter_cloud_batch_begin(self._h, n, descs, pp, lp, C.byref(ticket)))
+        return ticket.value
+
+    def filter_cloud_batch_wait(self, ticket):
+        _check(self._l.gg_filter_cloud_batch_wait(self._h, ticket))
 
     def synchronize(self):
         _check(self._l.gg_synchronize(self._h))

@@ -40,7 +40,7 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 constexpr int kStreams = 8;   // upper bound; GG_STREAMS (default 4) picks how many are used
-constexpr int kRing = 64;
+constexpr int kRing = 256;
 
 // CUDA-event pairs around every kernel launch while profiling is enabled.
 struct EventProfiler : gg::Profiler {
@@ -127,17 +127,24 @@ class HostPacker {
     }
     int threads() const { return (int)workers_.size(); }
 
-    // jobs must stay alive until wait_all(); chunks are handed out in job order
+    // jobs must stay alive until every job is either packed or claimed raw; chunks go out in job order
     void start(std::vector<PackJob>* jobs) {
         while (busy_.load(std::memory_order_acquire) != 0) std::this_thread::yield();  // stragglers of the previous run
         chunks_.clear();
+        first_chunk_.clear();
         for (size_t j = 0; j < jobs->size(); ++j) {
             PackJob& job = (*jobs)[j];
             const int nch = (int)std::max<size_t>(1, (job.n + kChunk - 1) / kChunk);
             job.remaining.store(nch, std::memory_order_relaxed);
+            first_chunk_.push_back(chunks_.size());
             for (int c = 0; c < nch; ++c) chunks_.push_back({(int)j, c});
         }
-        next_.store(0, std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> g(claim_mu_);
+            next_ = 0;
+            limit_ = chunks_.size();
+            raw_from_ = (int)jobs->size();
+        }
         {
             std::lock_guard<std::mutex> g(mu_);
             jobs_ = jobs;
@@ -145,12 +152,19 @@ class HostPacker {
         }
         cv_.notify_all();
     }
-    // the calling thread helps until the job is packed
-    void wait_job(PackJob& job) {
-        while (job.remaining.load(std::memory_order_acquire) > 0) {
-            if (!work_one()) std::this_thread::yield();
-        }
+    // Take the last job nobody has started packing yet out of the packers' hands (it will be sent as
+    // plain 32-byte records).  Returns its index or -1.
+    int claim_raw_from_back() {
+        std::lock_guard<std::mutex> g(claim_mu_);
+        if (raw_from_ <= 0) return -1;
+        const int j = raw_from_ - 1;
+        if (first_chunk_[j] < next_) return -1;  // a packer is already on it
+        raw_from_ = j;
+        limit_ = first_chunk_[j];
+        return j;
     }
+    bool packed(const PackJob& job) const { return job.remaining.load(std::memory_order_acquire) <= 0; }
+    bool help() { return work_one(); }  // the calling thread packs one chunk if any is left
 
     static void pack_range(const gg_point* src, size_t n, unsigned char* dst, size_t i0, size_t i1) {
         gg::pack_cloud_range(src, n, dst, i0, i1);
@@ -160,8 +174,12 @@ class HostPacker {
     bool work_one() {
         std::vector<PackJob>* jobs = jobs_;
         if (!jobs) return false;
-        const size_t c = next_.fetch_add(1, std::memory_order_relaxed);
-        if (c >= chunks_.size()) return false;
+        size_t c;
+        {
+            std::lock_guard<std::mutex> g(claim_mu_);
+            if (next_ >= limit_) return false;
+            c = next_++;
+        }
         PackJob& job = (*jobs)[chunks_[c].first];
         const size_t i0 = (size_t)chunks_[c].second * kChunk;
         pack_range(job.src, job.n, job.dst, i0, std::min(job.n, i0 + kChunk));
@@ -184,11 +202,13 @@ class HostPacker {
         }
     }
     std::vector<std::thread> workers_;
-    std::mutex mu_;
+    std::mutex mu_, claim_mu_;
     std::condition_variable cv_;
     std::vector<PackJob>* jobs_ = nullptr;
     std::vector<std::pair<int, int>> chunks_;
-    std::atomic<size_t> next_{0};
+    std::vector<size_t> first_chunk_;
+    size_t next_ = 0, limit_ = 0;
+    int raw_from_ = 0;
     std::atomic<int> busy_{0};
     uint64_t epoch_ = 0;
     bool stop_ = false;
@@ -202,7 +222,7 @@ struct SlotState {
     bool ran = false;
     bool output_valid = false;
     const gg_point* src = nullptr;  // caller-owned device cloud of the last scan (null: the slot's own buffer)
-    bool packed_input = false;      // last scan came through the packed host path (no 32-byte records on the device)
+    const float* packed_input = nullptr;  // last scan came through the packed host path (no 32-byte records on the device)
 };
 
 }  // namespace
@@ -235,13 +255,28 @@ struct gg_handle_s {
     float* d_image = nullptr;        // f3: terrain image staging (N * N * 3)
     unsigned long long* d_eval = nullptr;  // f4: [EVAL_LABELS][2] tallies
     HostPacker* packer = nullptr;    // created on the first packed batch call
-    unsigned char* h_packed = nullptr;  // pinned staging, [n_slots][14 * pcap]
+    // gg_filter_cloud_batch[_begin] alternates between two sets of input / label buffers ("parity"), so the
+    // clouds of batch t+1 can be packed and copied while the kernels of batch t still read theirs
+    unsigned char* h_packed[2] = {};   // pinned staging, [n_slots][14 * pcap]
+    unsigned char* in_packed[2] = {};  // device, same shape
+    gg_point* in_raw[2] = {};          // device 32-byte records; [0] is the slots' own buffer (view.points)
+    uint8_t* labels_buf[2] = {};       // [0] is the buffer the handle was created with
+    int batch_parity = 0;
+    bool batch_outstanding[2] = {};
+    cudaEvent_t batch_done[2] = {};    // on copy_out: kernels and label copies of the batch have finished
     int host_pack = 1;               // GG_HOST_PACK=0 sends the 32-byte records as they are
-    // Packing only pays when enough host cores are actually available (shared hosts, CPU quotas), so
-    // unless GG_HOST_PACK / GG_HOST_THREADS pin the choice, the first batch calls measure both ways:
-    // calls 0-1 packed, calls 2-3 plain 32-byte DMA, then the faster one (seconds per point) stays.
-    int pack_tune_calls = 0;         // -1: choice pinned
-    double pack_best[2] = {1e30, 1e30};
+    int launch_unit = 32;            // GG_LAUNCH_UNIT: scans per kernel launch set in gg_filter_cloud_batch
+    int host_pack_mix = 1;           // GG_HOST_PACK=1 pins "pack everything"; default: pack and send raw side by side
+    cudaStream_t copy_in[8] = {}, copy_out = nullptr;  // H2D / D2H of gg_filter_cloud_batch, never behind kernels
+    int n_copy_in = 4;                                   // GG_COPY_STREAMS
+    int main_help = 1;                                   // GG_MAIN_HELP
+    bool inputs_busy = false;  // asynchronous work that reads or writes the slots' input buffers may be in flight
+    std::vector<cudaEvent_t> batch_ev;                    // unit hand-over events of gg_filter_cloud_batch
+    cudaEvent_t raw_ev[8] = {};      // throttle of the raw copies issued by the mixing loop
+    int raw_depth = 4;               // GG_RAW_DEPTH: raw copies in flight before the loop stops claiming more
+    size_t last_raw = 0, last_packed = 0;  // scans sent raw / packed by the last batch call
+    size_t last_raw_bytes = 0, last_packed_bytes = 0;
+    size_t last_feed_us = 0, last_total_us = 0;  // host time until the last cloud was enqueued / until everything was done
     EventProfiler* prof = nullptr;   // non-null while profiling is enabled
     double prof_ms[gg::K_NUM] = {};
     uint32_t prof_count[gg::K_NUM] = {};
@@ -344,7 +379,7 @@ void fill_params(gg_handle h, const gg_scan_desc& d, gg::SlotParams& p, const gg
 
 // enqueue the kernels of `count` scans, each group of slots on its own stream
 int run_scans_grouped(gg_handle h, int count, const gg_scan_desc* scans, int stop_after, const gg_point* const* dev_points = nullptr,
-                      bool packed = false, int only_group = -1) {
+                      const float* const* packed_ptrs = nullptr, uint8_t* labels_base = nullptr) {
     if (count <= 0) return GG_OK;
     if (count > h->n_slots) return fail(GG_E_ARG, "count %d exceeds the number of slots %d", count, h->n_slots);
     int rc;
@@ -354,16 +389,17 @@ int run_scans_grouped(gg_handle h, int count, const gg_scan_desc* scans, int sto
         if (!h->slots[d.slot].have_map) return fail(GG_E_STATE, "slot %d: map not initialised", d.slot);
         if (d.n_points > h->pcap) return fail(GG_E_ARG, "slot %d: %zu points exceed capacity %zu", d.slot, d.n_points, h->pcap);
     }
+    gg::View view = h->view;
+    if (labels_base) view.labels = labels_base;
     for (int g = 0; g < h->n_streams; ++g) {
-        if (only_group >= 0 && g != only_group) continue;
         gg::SlotParams *hp = nullptr, *dp = nullptr;
         int pos = 0, m = 0, max_points = 0;
         for (int i = 0; i < count; ++i) {
             const gg_scan_desc& d = scans[i];
             if (stream_index(h, d.slot) != g) continue;
             if (m == 0 && (rc = ring_acquire(h, &hp, &dp, &pos))) return rc;
-            fill_params(h, d, hp[m], dev_points ? dev_points[i] : nullptr,
-                        packed ? reinterpret_cast<const float*>(h->view.packed + (size_t)d.slot * 14 * h->pcap) : nullptr);
+            const float* packed = packed_ptrs ? packed_ptrs[i] : nullptr;
+            fill_params(h, d, hp[m], dev_points ? dev_points[i] : nullptr, packed);
             ++m;
             max_points = std::max(max_points, (int)d.n_points);
             SlotState& s = h->slots[d.slot];
@@ -377,7 +413,7 @@ int run_scans_grouped(gg_handle h, int count, const gg_scan_desc* scans, int sto
         if (m == 0) continue;
         cudaStream_t st = h->streams[g];
         if ((rc = ring_commit(h, pos, m, st))) return rc;
-        h->launches += gg::launch_scan_pipeline(h->view, dp, m, max_points, stop_after, st, h->prof);
+        h->launches += gg::launch_scan_pipeline(view, dp, m, max_points, stop_after, st, h->prof);
         GG_CUDA(cudaGetLastError());
         if ((rc = ring_release(h, pos, st))) return rc;
     }
@@ -663,9 +699,13 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
         }
     }
 
+    if (const char* e = getenv("GG_LAUNCH_UNIT")) h->launch_unit = std::max(1, atoi(e));
+    if (const char* e = getenv("GG_COPY_STREAMS")) h->n_copy_in = std::min(8, std::max(1, atoi(e)));
+    if (const char* e = getenv("GG_MAIN_HELP")) h->main_help = atoi(e);
+    if (const char* e = getenv("GG_RAW_DEPTH")) h->raw_depth = std::min(8, std::max(1, atoi(e)));
     if (const char* e = getenv("GG_HOST_PACK")) {
         h->host_pack = atoi(e) ? 1 : 0;
-        h->pack_tune_calls = -1;
+        h->host_pack_mix = 0;
     }
     v.packed = nullptr;
     if (stream) {
@@ -694,7 +734,16 @@ int gg_destroy(gg_handle h) {
     delete h->prof;
     delete h->packer;
     if (h->d_raw) cudaFree(h->d_raw);
-    if (h->h_packed) cudaFreeHost(h->h_packed);
+    for (int e = 0; e < 2; ++e) {
+        if (h->h_packed[e]) cudaFreeHost(h->h_packed[e]);
+        if (h->batch_done[e]) cudaEventDestroy(h->batch_done[e]);
+    }
+    for (int e = 0; e < 8; ++e)
+        if (h->raw_ev[e]) cudaEventDestroy(h->raw_ev[e]);
+    for (cudaEvent_t e : h->batch_ev) cudaEventDestroy(e);
+    for (int e = 0; e < 8; ++e)
+        if (h->copy_in[e]) cudaStreamDestroy(h->copy_in[e]);
+    if (h->copy_out) cudaStreamDestroy(h->copy_out);
     for (void* p : h->dev_allocs) cudaFree(p);
     if (h->h_ring) cudaFreeHost(h->h_ring);
     for (int i = 0; i < kRing; ++i)
@@ -817,6 +866,7 @@ int gg_upload_points(gg_handle h, int slot, const gg_point* points, size_t n) {
     if (rc) return rc;
     if (n > h->pcap) return fail(GG_E_ARG, "%zu points exceed capacity %zu", n, h->pcap);
     if (n && !points) return fail(GG_E_ARG, "null points");
+    h->inputs_busy = true;
     GG_CUDA(cudaSetDevice(h->device));
     if (n) GG_CUDA(cudaMemcpyAsync(h->view.points + (size_t)slot * h->pcap, points, n * sizeof(gg_point), cudaMemcpyHostToDevice, stream_of(h, slot)));
     h->slots[slot].n_points = n;
@@ -826,6 +876,7 @@ int gg_upload_points(gg_handle h, int slot, const gg_point* points, size_t n) {
 int gg_run_scans(gg_handle h, int count, const gg_scan_desc* scans, int stop_after) {
     if (!h || !scans) return fail(GG_E_ARG, "null argument");
     if (stop_after < 0 || stop_after > 3) return fail(GG_E_ARG, "stop_after must be 0..3");
+    h->inputs_busy = true;
     GG_CUDA(cudaSetDevice(h->device));
     return run_scans_grouped(h, count, scans, stop_after);
 }
@@ -833,6 +884,7 @@ int gg_run_scans(gg_handle h, int count, const gg_scan_desc* scans, int stop_aft
 int gg_run_scans_device(gg_handle h, int count, const gg_scan_desc* scans, const gg_point* const* dev_points, int stop_after) {
     if (!h || !scans || !dev_points) return fail(GG_E_ARG, "null argument");
     if (stop_after < 0 || stop_after > 3) return fail(GG_E_ARG, "stop_after must be 0..3");
+    h->inputs_busy = true;
     for (int i = 0; i < count; ++i)
         if (!dev_points[i] && scans[i].n_points) return fail(GG_E_ARG, "scan %d: null device cloud", i);
     GG_CUDA(cudaSetDevice(h->device));
@@ -851,6 +903,7 @@ int gg_upload_cloud_msg(gg_handle h, int slot, const void* data, size_t n_points
         if ((f < 3 && field_offsets[f] < 0) || field_offsets[f] + width > point_step) return fail(GG_E_ARG, "field %d does not fit point_step", f);
     }
     GG_CUDA(cudaSetDevice(h->device));
+    h->inputs_busy = true;
     cudaStream_t st = stream_of(h, slot);
     const size_t bytes = n_points * (size_t)point_step;
     if (bytes > h->d_raw_cap) {
@@ -911,7 +964,7 @@ int gg_eval_accumulate(gg_handle h, int slot) {
     hp[0].slot = slot;
     hp[0].n_points = (int)s.n_points;
     hp[0].src = s.src ? s.src : h->view.points + (size_t)slot * h->pcap;
-    hp[0].packed = s.packed_input ? reinterpret_cast<const float*>(h->view.packed + (size_t)slot * 14 * h->pcap) : nullptr;
+    hp[0].packed = s.packed_input;
     if ((rc = ring_commit(h, pos, 1, st))) return rc;
     h->launches += gg::launch_eval(h->view, dp, h->d_eval, st, h->prof);
     GG_CUDA(cudaGetLastError());
@@ -985,6 +1038,9 @@ int gg_synchronize(gg_handle h) {
     if (!h) return fail(GG_E_ARG, "null handle");
     GG_CUDA(cudaSetDevice(h->device));
     for (int i = 0; i < h->n_streams; ++i) GG_CUDA(cudaStreamSynchronize(h->streams[i]));
+    if (h->copy_out) GG_CUDA(cudaStreamSynchronize(h->copy_out));
+    h->batch_outstanding[0] = h->batch_outstanding[1] = false;
+    h->inputs_busy = false;
     return GG_OK;
 }
 
@@ -1027,9 +1083,44 @@ int gg_filter_cloud(gg_handle h, int slot, const gg_point* points, size_t n, con
     return GG_OK;
 }
 
-int gg_filter_cloud_batch(gg_handle h, int count, const gg_scan_desc* scans, const gg_point* const* points, uint8_t* const* labels_out) {
+namespace {
+
+int batch_wait(gg_handle h, int parity) {
+    if (h->batch_outstanding[parity]) {
+        GG_CUDA(cudaEventSynchronize(h->batch_done[parity]));
+        h->batch_outstanding[parity] = false;
+    }
+    return GG_OK;
+}
+
+// streams, events and the second buffer set of the batch path
+int batch_prepare(gg_handle h) {
+    int rc;
+    if (!h->copy_out) {
+        for (int e = 0; e < 8; ++e) GG_CUDA(cudaEventCreateWithFlags(&h->raw_ev[e], cudaEventDisableTiming));
+        for (int e = 0; e < 2; ++e) GG_CUDA(cudaEventCreateWithFlags(&h->batch_done[e], cudaEventDisableTiming));
+        for (int e = 0; e < h->n_copy_in; ++e) GG_CUDA(cudaStreamCreateWithFlags(&h->copy_in[e], cudaStreamNonBlocking));
+        GG_CUDA(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+        h->in_raw[0] = h->view.points;
+        h->labels_buf[0] = h->view.labels;
+    }
+    if (h->host_pack && !h->h_packed[0]) {
+        if ((rc = dev_alloc(h, &h->in_raw[1], (size_t)h->n_slots * h->pcap))) return rc;
+        if ((rc = dev_alloc(h, &h->labels_buf[1], (size_t)h->n_slots * h->pcap))) return rc;
+        for (int e = 0; e < 2; ++e) {
+            GG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->h_packed[e]), (size_t)h->n_slots * 14 * h->pcap, cudaHostAllocDefault));
+            if ((rc = dev_alloc(h, &h->in_packed[e], (size_t)h->n_slots * 14 * h->pcap))) return rc;
+        }
+    }
+    return GG_OK;
+}
+
+}  // namespace
+
+int gg_filter_cloud_batch_begin(gg_handle h, int count, const gg_scan_desc* scans, const gg_point* const* points, uint8_t* const* labels_out,
+                                int* ticket) {
     if (!h || !scans || !points) return fail(GG_E_ARG, "null argument");
-    if (count <= 0) return GG_OK;
+    if (count < 0) return fail(GG_E_ARG, "negative count");
     if (count > h->n_slots) return fail(GG_E_ARG, "count exceeds slots");
     GG_CUDA(cudaSetDevice(h->device));
     int rc;
@@ -1038,39 +1129,54 @@ int gg_filter_cloud_batch(gg_handle h, int count, const gg_scan_desc* scans, con
         if ((rc = check_slot(h, d.slot))) return rc;
         if (d.n_points > h->pcap) return fail(GG_E_ARG, "slot %d: too many points", d.slot);
         if (d.n_points && !points[i]) return fail(GG_E_ARG, "scan %d: null cloud", i);
+        if (!h->slots[d.slot].have_map) return fail(GG_E_STATE, "slot %d: map not initialised", d.slot);
     }
     if (h->host_pack && !h->packer) {
-        // packing pays only with enough host threads; with few (e.g. 8 ranks sharing a small CPU
-        // quota) the plain 32-byte DMA is faster.  GG_HOST_THREADS forces a count.
+        // GG_HOST_THREADS forces a thread count; by default all usable CPUs (affinity, cgroup quota,
+        // shared between the local ranks) but one
         int threads = 0;
         if (const char* e = getenv("GG_HOST_THREADS")) threads = atoi(e);
         if (threads <= 0) {
             int local = 1;
             if (const char* e = getenv("LOCAL_WORLD_SIZE")) local = std::max(1, atoi(e));
             threads = std::min(48, gg::usable_cpus() / local - 1);
-            if (threads < 6) {  // hopeless: ~0.14 Gpts/s per packing thread vs ~1.4 Gpts/s of plain 32-byte DMA
-                h->host_pack = 0;
-                h->pack_tune_calls = -1;
-            }
-        } else {
-            h->pack_tune_calls = -1;
         }
-        if (h->host_pack) h->packer = new HostPacker(std::max(1, threads));
+        if (threads < 1)
+            h->host_pack = 0;
+        else
+            h->packer = new HostPacker(threads);
     }
-    size_t total_points = 0;
-    for (int i = 0; i < count; ++i) total_points += scans[i].n_points;
-    const bool tuning = h->pack_tune_calls >= 0 && h->pack_tune_calls < 4 && h->packer && total_points > 0;
-    const bool use_pack = h->host_pack && h->packer && (!tuning || h->pack_tune_calls < 2);
+    if ((rc = batch_prepare(h))) return rc;
+    while ((int)h->batch_ev.size() < h->n_streams) {  // [0, n_streams): one event per compute stream
+        cudaEvent_t ev;
+        GG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        h->batch_ev.push_back(ev);
+    }
+    const int par = h->host_pack ? h->batch_parity : 0;
+    // the batch that used this buffer set two calls ago must be complete (it normally is, long since)
+    if ((rc = batch_wait(h, par))) return rc;
+    h->last_raw = h->last_packed = h->last_raw_bytes = h->last_packed_bytes = 0;
     const auto t_begin = std::chrono::steady_clock::now();
-    if (use_pack) {
-        // Packed path: worker threads repack the clouds (14 useful bytes of every 32-byte record)
-        // into pinned staging memory, group by group; as soon as a cloud is packed its H2D copy is
-        // enqueued, and as soon as a stream group is complete its kernels are launched, so packing,
-        // PCIe traffic and kernels of different groups overlap.
-        if (!h->h_packed) {
-            GG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->h_packed), (size_t)h->n_slots * 14 * h->pcap, cudaHostAllocDefault));
-            if ((rc = dev_alloc(h, &h->view.packed, (size_t)h->n_slots * 14 * h->pcap))) return rc;
-        }
+    auto us_since = [&] { return (size_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_begin).count(); };
+    if (h->host_pack) {
+        // Two ways to get a cloud across PCIe: repacked by host worker threads into x | y | z | ring
+        // (14 useful bytes of every 32-byte record, costs CPU time) or as it is (costs bus time).  Both
+        // resources are used at once: the packers walk the scans from the front; whenever fewer than
+        // raw_depth raw copies of this loop are pending, the calling thread takes the LAST scan nobody has
+        // started packing and sends it raw.  Whatever the CPU quota of the host, neither the packers
+        // nor the bus sit idle.
+        //
+        // All clouds go through a few copy streams and all labels come back through another one, so a
+        // transfer never queues behind kernels.  Events hand the scans over: copies -> kernels (the
+        // stream of the slot) -> label read-back.  Kernels are enqueued for `launch_unit` delivered scans
+        // of a stream group at a time, so that only the kernels of the last few scans run after the
+        // transfers have ended.
+        unsigned char* const hpk = h->h_packed[par];
+        unsigned char* const dpk = h->in_packed[par];
+        gg_point* const draw = h->in_raw[par];
+        uint8_t* const dlab = h->labels_buf[par];
+        h->view.labels = dlab;  // what gg_download_labels / gg_get_output read after this batch
+        const int KC = h->n_copy_in;
         std::vector<int> order;
         for (int g = 0; g < h->n_streams; ++g)
             for (int i = 0; i < count; ++i)
@@ -1080,42 +1186,147 @@ int gg_filter_cloud_batch(gg_handle h, int count, const gg_scan_desc* scans, con
             const gg_scan_desc& d = scans[order[k]];
             jobs[k].src = points[order[k]];
             jobs[k].n = d.n_points;
-            jobs[k].dst = h->h_packed + (size_t)d.slot * 14 * h->pcap;
+            jobs[k].dst = hpk + (size_t)d.slot * 14 * h->pcap;
         }
+        if (h->inputs_busy) {  // earlier asynchronous calls may still use the slots' own input buffers
+            for (int g = 0; g < h->n_streams; ++g) {
+                GG_CUDA(cudaEventRecord(h->batch_ev[g], h->streams[g]));
+                for (int c = 0; c < KC; ++c) GG_CUDA(cudaStreamWaitEvent(h->copy_in[c], h->batch_ev[g], 0));
+            }
+        }
+        size_t ev_used = h->n_streams;
+        auto next_event = [&](cudaEvent_t* ev) -> int {
+            if (ev_used == h->batch_ev.size()) {
+                cudaEvent_t e;
+                GG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                h->batch_ev.push_back(e);
+            }
+            *ev = h->batch_ev[ev_used++];
+            return GG_OK;
+        };
+        std::vector<std::vector<int>> pending(h->n_streams);  // delivered, kernels not yet enqueued (positions in `order`)
+        std::vector<gg_scan_desc> ud;
+        std::vector<const gg_point*> usrc;
+        std::vector<const float*> upk;
+        std::vector<unsigned char> sent_packed(count, 0);
+        auto flush = [&](int g) -> int {
+            std::vector<int>& pg = pending[g];
+            if (pg.empty()) return GG_OK;
+            ud.clear();
+            usrc.clear();
+            upk.clear();
+            for (int k : pg) {
+                const gg_scan_desc& d = scans[order[k]];
+                ud.push_back(d);
+                usrc.push_back(draw + (size_t)d.slot * h->pcap);
+                upk.push_back(sent_packed[k] ? reinterpret_cast<const float*>(dpk + (size_t)d.slot * 14 * h->pcap) : nullptr);
+            }
+            cudaStream_t st = h->streams[g];
+            cudaEvent_t ev;
+            int rc2;
+            for (int c = 0; c < KC; ++c) {  // the clouds are spread over all copy streams
+                if ((rc2 = next_event(&ev))) return rc2;
+                GG_CUDA(cudaEventRecord(ev, h->copy_in[c]));
+                GG_CUDA(cudaStreamWaitEvent(st, ev, 0));
+            }
+            if ((rc2 = run_scans_grouped(h, (int)ud.size(), ud.data(), 0, usrc.data(), upk.data(), dlab))) return rc2;
+            if (labels_out) {  // the labels travel under the remaining H2D traffic
+                if ((rc2 = next_event(&ev))) return rc2;
+                GG_CUDA(cudaEventRecord(ev, st));
+                GG_CUDA(cudaStreamWaitEvent(h->copy_out, ev, 0));
+                for (int k : pg)
+                    if (labels_out[order[k]] && scans[order[k]].n_points)
+                        GG_CUDA(cudaMemcpyAsync(labels_out[order[k]], dlab + (size_t)scans[order[k]].slot * h->pcap, scans[order[k]].n_points,
+                                                cudaMemcpyDeviceToHost, h->copy_out));
+            }
+            pg.clear();
+            return GG_OK;
+        };
+        auto delivered = [&](int k) -> int {
+            const int g = stream_index(h, scans[order[k]].slot);
+            pending[g].push_back(k);
+            return (int)pending[g].size() >= h->launch_unit ? flush(g) : GG_OK;
+        };
         h->packer->start(&jobs);
-        for (int k = 0; k < count; ++k) {
-            const gg_scan_desc& d = scans[order[k]];
-            h->packer->wait_job(jobs[k]);
-            const size_t n_pad = (d.n_points + 7) & ~(size_t)7;
-            if (d.n_points)
-                GG_CUDA(cudaMemcpyAsync(h->view.packed + (size_t)d.slot * 14 * h->pcap, jobs[k].dst, 14 * n_pad, cudaMemcpyHostToDevice,
-                                        stream_of(h, d.slot)));
-            const int g = stream_index(h, d.slot);
-            if (k + 1 == count || stream_index(h, scans[order[k + 1]].slot) != g)
-                if ((rc = run_scans_grouped(h, count, scans, 0, nullptr, true, g))) return rc;
+        int front = 0, back = count, raw_issued = 0, n_copies = 0;
+        while (front < back) {
+            if (h->packer->packed(jobs[front])) {
+                const gg_scan_desc& d = scans[order[front]];
+                const size_t n_pad = (d.n_points + 7) & ~(size_t)7;
+                if (d.n_points)
+                    GG_CUDA(cudaMemcpyAsync(dpk + (size_t)d.slot * 14 * h->pcap, jobs[front].dst, 14 * n_pad, cudaMemcpyHostToDevice,
+                                            h->copy_in[n_copies++ % KC]));
+                sent_packed[front] = 1;
+                ++h->last_packed;
+                h->last_packed_bytes += 14 * n_pad;
+                if ((rc = delivered(front))) return rc;
+                ++front;
+                continue;
+            }
+            const bool bus_free = h->host_pack_mix && (raw_issued < h->raw_depth || cudaEventQuery(h->raw_ev[raw_issued % h->raw_depth]) == cudaSuccess);
+            int j = bus_free ? h->packer->claim_raw_from_back() : -1;
+            if (j >= 0) {
+                const gg_scan_desc& d = scans[order[j]];
+                if (d.n_points)
+                    GG_CUDA(cudaMemcpyAsync(draw + (size_t)d.slot * h->pcap, jobs[j].src, d.n_points * sizeof(gg_point), cudaMemcpyHostToDevice,
+                                            h->copy_in[n_copies % KC]));
+                GG_CUDA(cudaEventRecord(h->raw_ev[raw_issued % h->raw_depth], h->copy_in[n_copies++ % KC]));
+                ++raw_issued;
+                ++h->last_raw;
+                h->last_raw_bytes += d.n_points * sizeof(gg_point);
+                back = j;
+                if ((rc = delivered(j))) return rc;
+                continue;
+            }
+            // nothing to enqueue: with the raw queue full (or no mixing) this thread packs a chunk as well
+            if ((h->host_pack_mix && (bus_free || !h->main_help)) || !h->packer->help()) std::this_thread::yield();
         }
+        for (int g = 0; g < h->n_streams; ++g)
+            if ((rc = flush(g))) return rc;
+        h->batch_parity ^= 1;
     } else {
-        // H2D of every 32-byte cloud on its slot's stream, then the kernels of each stream group
+        // H2D of every 32-byte cloud on its slot's stream, then the kernels of each stream group: everything is
+        // stream-ordered, one buffer set is enough
         for (int i = 0; i < count; ++i) {
             const gg_scan_desc& d = scans[i];
             if (d.n_points)
                 GG_CUDA(cudaMemcpyAsync(h->view.points + (size_t)d.slot * h->pcap, points[i], d.n_points * sizeof(gg_point), cudaMemcpyHostToDevice,
                                         stream_of(h, d.slot)));
         }
+        h->last_raw = (size_t)count;
+        for (int i = 0; i < count; ++i) h->last_raw_bytes += scans[i].n_points * sizeof(gg_point);
         if ((rc = run_scans_grouped(h, count, scans, 0))) return rc;
+        if (labels_out)
+            for (int i = 0; i < count; ++i)
+                if (labels_out[i] && scans[i].n_points)
+                    GG_CUDA(cudaMemcpyAsync(labels_out[i], h->view.labels + (size_t)scans[i].slot * h->pcap, scans[i].n_points, cudaMemcpyDeviceToHost,
+                                            stream_of(h, scans[i].slot)));
     }
-    if (labels_out)
-        for (int i = 0; i < count; ++i)
-            if (labels_out[i] && scans[i].n_points)
-                GG_CUDA(cudaMemcpyAsync(labels_out[i], h->view.labels + (size_t)scans[i].slot * h->pcap, scans[i].n_points, cudaMemcpyDeviceToHost,
-                                        stream_of(h, scans[i].slot)));
+    // batch_done: everything enqueued so far on the compute streams and on the label stream
+    for (int g = 0; g < h->n_streams; ++g) {
+        GG_CUDA(cudaEventRecord(h->batch_ev[g], h->streams[g]));
+        GG_CUDA(cudaStreamWaitEvent(h->copy_out, h->batch_ev[g], 0));
+    }
+    GG_CUDA(cudaEventRecord(h->batch_done[par], h->copy_out));
+    h->batch_outstanding[par] = true;
+    if (ticket) *ticket = par;
+    h->last_feed_us = us_since();
+    return GG_OK;
+}
+
+int gg_filter_cloud_batch_wait(gg_handle h, int ticket) {
+    if (!h) return fail(GG_E_ARG, "null handle");
+    if (ticket < 0 || ticket > 1) return fail(GG_E_ARG, "bad ticket %d", ticket);
+    GG_CUDA(cudaSetDevice(h->device));
+    return batch_wait(h, ticket);
+}
+
+int gg_filter_cloud_batch(gg_handle h, int count, const gg_scan_desc* scans, const gg_point* const* points, uint8_t* const* labels_out) {
+    const auto t_begin = std::chrono::steady_clock::now();
+    int rc = gg_filter_cloud_batch_begin(h, count, scans, points, labels_out, nullptr);
+    if (rc) return rc;
     rc = gg_synchronize(h);
-    if (tuning && rc == GG_OK) {
-        const double per_point = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count() / (double)total_points;
-        double& best = h->pack_best[use_pack ? 1 : 0];
-        best = std::min(best, per_point);
-        if (++h->pack_tune_calls == 4) h->host_pack = h->pack_best[1] < h->pack_best[0] ? 1 : 0;
-    }
+    h->last_total_us = (size_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_begin).count();
     return rc;
 }
 
@@ -1163,10 +1374,17 @@ int gg_host_pack_cloud(const gg_point* src, size_t n, unsigned char* dst) {
 }
 
 // number of host threads that repack clouds in gg_filter_cloud_batch (0: packing disabled or not used yet)
-int gg_host_pack_threads(gg_handle h) {
-    if (!h || !h->host_pack || !h->packer) return 0;
-    if (h->pack_tune_calls >= 0 && h->pack_tune_calls < 4) return -(h->packer->threads() + 1);  // still measuring
-    return h->packer->threads() + 1;
+int gg_host_pack_threads(gg_handle h) { return (h && h->host_pack && h->packer) ? h->packer->threads() + 1 : 0; }
+
+int gg_last_batch_transfer(gg_handle h, size_t info[6]) {
+    if (!h || !info) return fail(GG_E_ARG, "null argument");
+    info[0] = h->last_packed;
+    info[1] = h->last_raw;
+    info[2] = h->last_packed_bytes;
+    info[3] = h->last_raw_bytes;
+    info[4] = h->last_feed_us;
+    info[5] = h->last_total_us;
+    return GG_OK;
 }
 
 int gg_get_layer(gg_handle h, int slot, const char* name, float* dst) {

@@ -451,6 +451,25 @@ static void pack_sse2(const gg_point* src, size_t n, unsigned char* dst, size_t 
     _mm_sfence();
 }
 
+// 32 records (1 KB) per iteration: every destination cache line (2 of x, y and z each, 1 of rings) is
+// written completely by back-to-back streaming stores, so each write-combining buffer drains as one full
+// line.  The rings come out of the upper record halves by the same in-lane transpose as the coordinates.
+__attribute__((target("avx2"))) static inline void pack8_avx2(const gg_point* p, float* x, float* y, float* z, __m256i& ring_dwords) {
+    // lane 0: records 0..3, lane 1: records 4..7; transpose 4x4 inside each 128-bit lane
+    const __m256 a = _mm256_loadu2_m128(&p[4].x, &p[0].x), b = _mm256_loadu2_m128(&p[5].x, &p[1].x);
+    const __m256 c = _mm256_loadu2_m128(&p[6].x, &p[2].x), d = _mm256_loadu2_m128(&p[7].x, &p[3].x);
+    const __m256 t0 = _mm256_unpacklo_ps(a, b), t1 = _mm256_unpackhi_ps(a, b);
+    const __m256 t2 = _mm256_unpacklo_ps(c, d), t3 = _mm256_unpackhi_ps(c, d);
+    _mm256_stream_ps(x, _mm256_shuffle_ps(t0, t2, 0x44));  // x0..x3 | x4..x7
+    _mm256_stream_ps(y, _mm256_shuffle_ps(t0, t2, 0xEE));
+    _mm256_stream_ps(z, _mm256_shuffle_ps(t1, t3, 0x44));
+    // upper halves: intensity | ring (u16) + 2 padding bytes | padding | padding
+    const __m256 e = _mm256_loadu2_m128(&p[4].intensity, &p[0].intensity), f = _mm256_loadu2_m128(&p[5].intensity, &p[1].intensity);
+    const __m256 g = _mm256_loadu2_m128(&p[6].intensity, &p[2].intensity), h = _mm256_loadu2_m128(&p[7].intensity, &p[3].intensity);
+    const __m256 u0 = _mm256_unpacklo_ps(e, f), u2 = _mm256_unpacklo_ps(g, h);
+    ring_dwords = _mm256_and_si256(_mm256_castps_si256(_mm256_shuffle_ps(u0, u2, 0xEE)), _mm256_set1_epi32(0xffff));
+}
+
 __attribute__((target("avx2"))) static void pack_avx2(const gg_point* src, size_t n, unsigned char* dst, size_t i0, size_t i1) {
     const size_t n_pad = (n + 7) & ~(size_t)7;
     float* x = reinterpret_cast<float*>(dst);
@@ -458,24 +477,26 @@ __attribute__((target("avx2"))) static void pack_avx2(const gg_point* src, size_
     float* z = y + n_pad;
     uint16_t* r = reinterpret_cast<uint16_t*>(z + n_pad);
     size_t i = i0;
-    const size_t vec_end = i0 + ((std::min(i1, n) - i0) & ~(size_t)7);
-    for (; i < vec_end; i += 8) {
+    const size_t stop = std::min(i1, n);
+    const size_t end32 = i0 + ((stop - i0) & ~(size_t)31), end8 = i0 + ((stop - i0) & ~(size_t)7);
+    for (; i < end32; i += 32) {
         const gg_point* p = src + i;
-        _mm_prefetch(reinterpret_cast<const char*>(p + 32), _MM_HINT_NTA);
-        _mm_prefetch(reinterpret_cast<const char*>(p + 34), _MM_HINT_NTA);
-        _mm_prefetch(reinterpret_cast<const char*>(p + 36), _MM_HINT_NTA);
-        _mm_prefetch(reinterpret_cast<const char*>(p + 38), _MM_HINT_NTA);
-        // lane 0: records 0..3, lane 1: records 4..7; transpose 4x4 inside each 128-bit lane
-        const __m256 a = _mm256_loadu2_m128(&p[4].x, &p[0].x), b = _mm256_loadu2_m128(&p[5].x, &p[1].x);
-        const __m256 c = _mm256_loadu2_m128(&p[6].x, &p[2].x), d = _mm256_loadu2_m128(&p[7].x, &p[3].x);
-        const __m256 t0 = _mm256_unpacklo_ps(a, b), t1 = _mm256_unpackhi_ps(a, b);
-        const __m256 t2 = _mm256_unpacklo_ps(c, d), t3 = _mm256_unpackhi_ps(c, d);
-        _mm256_stream_ps(x + i, _mm256_shuffle_ps(t0, t2, 0x44));  // x0..x3 | x4..x7
-        _mm256_stream_ps(y + i, _mm256_shuffle_ps(t0, t2, 0xEE));
-        _mm256_stream_ps(z + i, _mm256_shuffle_ps(t1, t3, 0x44));
-        alignas(16) uint16_t rr[8];
-        for (int q = 0; q < 8; ++q) rr[q] = p[q].ring;
-        _mm_stream_si128(reinterpret_cast<__m128i*>(r + i), _mm_load_si128(reinterpret_cast<const __m128i*>(rr)));
+        for (int l = 0; l < 16; ++l) _mm_prefetch(reinterpret_cast<const char*>(p + 64) + 64 * l, _MM_HINT_NTA);  // 2 KB ahead
+        __m256i r0, r1, r2, r3;
+        // coordinates line by line: 16 records fill one 64-byte line of x, y and z each
+        pack8_avx2(p, x + i, y + i, z + i, r0);
+        pack8_avx2(p + 8, x + i + 8, y + i + 8, z + i + 8, r1);
+        pack8_avx2(p + 16, x + i + 16, y + i + 16, z + i + 16, r2);
+        pack8_avx2(p + 24, x + i + 24, y + i + 24, z + i + 24, r3);
+        // packus interleaves the 128-bit lanes of its operands: restore record order with a 64-bit permute
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(r + i), _mm256_permute4x64_epi64(_mm256_packus_epi32(r0, r1), 0xD8));
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(r + i + 16), _mm256_permute4x64_epi64(_mm256_packus_epi32(r2, r3), 0xD8));
+    }
+    for (; i < end8; i += 8) {
+        __m256i r0;
+        pack8_avx2(src + i, x + i, y + i, z + i, r0);
+        const __m256i w = _mm256_permute4x64_epi64(_mm256_packus_epi32(r0, r0), 0xD8);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(r + i), _mm256_castsi256_si128(w));
     }
     pack_tail(src, n, n_pad, x, y, z, r, i, i1);
     _mm_sfence();

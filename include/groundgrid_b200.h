@@ -143,12 +143,25 @@ int gg_filter_cloud(gg_handle h, int slot, const gg_point* points, size_t n, con
 /* Batched form of gg_filter_cloud: `count` independent scans (distinct slots), host buffers.
  * points[k] / labels_out[k] are per-scan host pointers (pinned memory makes the copies
  * asynchronous).  Copies and kernels of different scans overlap on internal streams.
- * PCIe is the bottleneck of this path, so by default (GG_HOST_PACK=1) host worker threads
- * (GG_HOST_THREADS) first repack every cloud into pinned staging memory as
- * x | y | z | ring (14 of the 32 bytes of a PointXYZIR record are used by the algorithm) and
- * only those bytes cross the bus; results are identical. */
+ * PCIe is the bottleneck of this path.  Host worker threads (GG_HOST_THREADS; default: the usable
+ * CPUs of the process minus one) repack clouds into pinned staging memory as x | y | z | ring
+ * (14 of the 32 bytes of a PointXYZIR record are used by the algorithm) so that only those bytes
+ * cross the bus, and while they are busy the calling thread sends the scans they have not reached
+ * yet as plain 32-byte records, so neither the packers nor the copy engine wait for the other.
+ * GG_HOST_PACK=1 packs every scan, GG_HOST_PACK=0 none.  Results are identical in all modes. */
 int gg_filter_cloud_batch(gg_handle h, int count, const gg_scan_desc* scans, const gg_point* const* points,
                           uint8_t* const* labels_out);
+
+/* The same call in two halves, for callers that keep the bus busy across batches: _begin returns as
+ * soon as every cloud has been handed to the copy engines and every kernel is enqueued; the labels of
+ * that batch are complete after _wait(ticket) (or gg_synchronize).  At most two batches are in
+ * flight: _begin first waits for the batch before the previous one.  points[k] and labels_out[k] of a
+ * batch must stay untouched until its _wait; gg_update_pose_batch for the next scans may be called
+ * right after _begin (stream order keeps roll -> scan -> roll -> scan per slot).  Other calls that
+ * touch the same slots need a gg_synchronize first. */
+int gg_filter_cloud_batch_begin(gg_handle h, int count, const gg_scan_desc* scans, const gg_point* const* points,
+                                uint8_t* const* labels_out, int* ticket);
+int gg_filter_cloud_batch_wait(gg_handle h, int ticket);
 
 /* Device-resident pipeline pieces (what gg_filter_cloud_batch is made of; used by bench.py to time
  * the kernels with the inputs already in HBM, and by the tests to check single phases):
@@ -222,6 +235,10 @@ int gg_set_map_position(gg_handle h, int slot, double x, double y);
 void* gg_stream(gg_handle h);
 int gg_num_streams(gg_handle h);
 int gg_host_pack_threads(gg_handle h);
+/* How the last gg_filter_cloud_batch call moved its clouds: info[0] scans repacked on the host,
+ * info[1] scans sent as 32-byte records, info[2] / info[3] the H2D bytes of either kind,
+ * info[4] host microseconds until the last cloud was enqueued, info[5] until the call returned. */
+int gg_last_batch_transfer(gg_handle h, size_t info[6]);
 int gg_fork_streams(gg_handle h);
 int gg_join_streams(gg_handle h);
 

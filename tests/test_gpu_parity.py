@@ -309,6 +309,56 @@ def test_batched_slots_match_single_and_are_deterministic():
         assert np.array_equal(g2.layer("ground", slot=b), g.layer("ground", slot=b))
 
 
+@pytest.mark.parametrize("unit", ["2", "32"])
+def test_overlapped_batches_begin_wait(monkeypatch, unit):
+    """gg_filter_cloud_batch_begin/_wait: the clouds of step t+1 are packed and copied while the kernels of
+    step t still run (two buffer sets); rolls in between; every step's labels and the final layers match."""
+    import torch
+
+    monkeypatch.setenv("GG_LAUNCH_UNIT", unit)
+    dim, res, B, steps = 99.0, 0.33, 5, 6
+    g = capi.GroundGridB200(dim, res, n_slots=B, max_points=131072, full_layers=False)
+    scenes = [synth.make_scene(seed=500 + b, stream_len=20.0) for b in range(B)]
+    clouds, host, labs = {}, {}, {}
+    for k in range(steps):
+        for b in range(B):
+            p, org = synth.scan_64(scenes[b], ego_xy=(0.9 * k, 0.3 * k * (b - 2)), seed=900 + 10 * k + b)
+            clouds[k, b] = (p, org)
+            host[k, b] = torch.from_numpy(np.ascontiguousarray(p).view(np.uint8).copy()).pin_memory()
+            labs[k, b] = torch.zeros(len(p), dtype=torch.uint8).pin_memory()
+    slots = np.arange(B, dtype=np.int32)
+    pending = None
+    for k in range(steps):
+        xy = np.array([[0.9 * k, 0.3 * k * (b - 2)] for b in range(B)])
+        Ts = np.stack([synth.base_from_map(x, y).reshape(12) for x, y in xy])
+        if k == 0:
+            for b in range(B):
+                g.init_map(xy[b, 0], xy[b, 1], 0.0, slot=b)
+        else:
+            g.update_pose_batch(slots, xy, Ts)
+        descs = g.make_descs(list(range(B)), [len(clouds[k, b][0]) for b in range(B)], [clouds[k, b][1] for b in range(B)], [0.0] * B)
+        ticket = g.filter_cloud_batch_begin(descs, [host[k, b].data_ptr() for b in range(B)], [labs[k, b].data_ptr() for b in range(B)])
+        if pending is not None:
+            g.filter_cloud_batch_wait(pending)
+        pending = ticket
+    g.filter_cloud_batch_wait(pending)
+    g.synchronize()
+    for b in range(B):
+        o = Oracle(dim, res)
+        for k in range(steps):
+            x, y = 0.9 * k, 0.3 * k * (b - 2)
+            if k == 0:
+                o.init_map(x, y, 0.0)
+            else:
+                o.update(x, y, synth.base_from_map(x, y))
+            want, _, _ = o.filter_cloud(clouds[k, b][0], clouds[k, b][1], 0.0, threads=1)
+            assert np.array_equal(labs[k, b].numpy(), want), f"slot {b} step {k}: {(labs[k, b].numpy() != want).sum()} labels differ"
+        for name in ("ground", "groundpatch", "variance", "points"):
+            r = diff_report(name, g.layer(name, slot=b), o.layer(name))
+            assert r is None, f"slot {b}: {r}"
+    g.close()
+
+
 def test_batch_path_with_and_without_host_packing(monkeypatch):
     import torch
 
@@ -316,8 +366,11 @@ def test_batch_path_with_and_without_host_packing(monkeypatch):
     scans = [synth.scan_64(synth.make_scene(seed=300 + b), seed=300 + b) for b in range(B)]
     hp = [torch.from_numpy(np.ascontiguousarray(p).view(np.uint8).copy()).pin_memory() for p, _ in scans]
     out = {}
-    for pack in ("1", "0"):
-        monkeypatch.setenv("GG_HOST_PACK", pack)
+    for pack in ("1", "0", "mix"):
+        if pack == "mix":      # default: packers and raw 32-byte copies side by side
+            monkeypatch.delenv("GG_HOST_PACK", raising=False)
+        else:
+            monkeypatch.setenv("GG_HOST_PACK", pack)
         g = capi.GroundGridB200(dim, res, n_slots=B, max_points=131072)
         hl = [torch.zeros(len(p), dtype=torch.uint8).pin_memory() for p, _ in scans]
         for b in range(B):
@@ -325,7 +378,10 @@ def test_batch_path_with_and_without_host_packing(monkeypatch):
         for rep in range(2):
             descs = g.make_descs(list(range(B)), [len(p) for p, _ in scans], [o for _, o in scans], [0.0] * B)
             g.filter_cloud_batch_ptrs(descs, [t.data_ptr() for t in hp], [t.data_ptr() for t in hl])
-        assert (g.host_pack_threads != 0) == (pack == "1")
+        assert (g.host_pack_threads != 0) == (pack != "0")
+        n_packed, n_raw, b_packed, b_raw = g.last_batch_transfer()[:4]
+        assert n_packed + n_raw == B and (pack != "1" or n_raw == 0) and (pack != "0" or n_packed == 0)
+        assert b_raw == sum(32 * len(scans[b][0]) for b in range(B)) if pack == "0" else b_packed + b_raw > 0
         out[pack] = [t.numpy().copy() for t in hl]
         g.close()
     for b in range(B):
@@ -333,7 +389,7 @@ def test_batch_path_with_and_without_host_packing(monkeypatch):
         o.init_map(0.0, 0.0, 0.0)
         for rep in range(2):
             want, _, _ = o.filter_cloud(scans[b][0], scans[b][1], 0.0, threads=1)
-        assert np.array_equal(out["1"][b], want) and np.array_equal(out["0"][b], want)
+        assert all(np.array_equal(out[k][b], want) for k in ("1", "0", "mix"))
 
 
 def test_error_codes():

@@ -244,10 +244,11 @@ def test_host_cloud_packing(n):
 
     rng = np.random.default_rng(n)
     pts = np.zeros(n, synth.POINT_DTYPE)
+    pts.view(np.uint8)[:] = 0xCD          # junk in the padding bytes of the records
     for c in "xyz":
         pts[c] = rng.standard_normal(n).astype(np.float32)
     pts["intensity"] = 7.0
-    pts["ring"] = rng.integers(0, 65535, n)
+    pts["ring"] = rng.integers(0, 65536, n)
     n_pad = (n + 7) & ~7
     raw = np.full(14 * n_pad + 64, 0xAB, np.uint8)
     off = (-raw.ctypes.data) % 32
