@@ -429,7 +429,7 @@ def main():
         pts_e2e = 0
         h2d = 0
         n_packed = n_raw = 0
-        feed_us = 0
+        feed_us = pack_us = wait_us = idle_us = 0
         for _ in range(args.steps):
             s = step_e2e()
             pts_e2e += int(pts_per_pose[s])
@@ -438,6 +438,9 @@ def main():
             n_raw += tr[1]
             h2d += tr[2] + tr[3]
             feed_us += tr[4]
+            pack_us += tr[6]
+            wait_us += tr[7]
+            idle_us += tr[8]
         drain_e2e()
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
@@ -449,6 +452,9 @@ def main():
                                     "ms_after_last_cloud_enqueued": tail_us / n_sync / 1e3, "api": "gg_filter_cloud_batch"},
                "host_pack_threads": max(0, g.host_pack_threads),
                "begin_call_ms": feed_us / args.steps / 1e3,
+               "begin_call_breakdown_ms": {"packer_threads_packing_sum": pack_us / args.steps / 1e3,
+                                           "packer_threads_waiting_for_slot_sum": wait_us / args.steps / 1e3,
+                                           "feeder_nothing_to_enqueue": idle_us / args.steps / 1e3},
                "scans_repacked_14B": n_packed, "scans_raw_32B": n_raw,
                "pcie_bytes_per_point": round(h2d / max(1, pts_e2e), 2)}
 

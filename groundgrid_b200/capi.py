@@ -258,8 +258,9 @@ class GroundGridB200:
         return self._l.gg_host_pack_threads(self._h)
 
     def last_batch_transfer(self):
-        """(scans packed, scans raw, packed H2D bytes, raw H2D bytes, feed us, total us) of the last batch call."""
-        info = (C.c_size_t * 6)()
+        """(scans packed, scans raw, packed H2D bytes, raw H2D bytes, feed us, total us, packers' pack us,
+        packers' slot-wait us, feeder idle us) of the last batch call."""
+        info = (C.c_size_t * 9)()
         _check(self._l.gg_last_batch_transfer(self._h, info))
         return tuple(int(v) for v in info)
 

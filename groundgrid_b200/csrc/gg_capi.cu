@@ -106,7 +106,6 @@ struct EventProfiler : gg::Profiler {
 struct PackJob {
     const gg_point* src = nullptr;
     size_t n = 0;
-    unsigned char* dst = nullptr;
     std::atomic<int> remaining{0};
 };
 
@@ -127,9 +126,24 @@ class HostPacker {
     }
     int threads() const { return (int)workers_.size(); }
 
-    // jobs must stay alive until every job is either packed or claimed raw; chunks go out in job order
-    void start(std::vector<PackJob>* jobs) {
+    // Staging ring: packed job number `seq` (counted over the lifetime of the handle) is written to slot
+    // seq % slots.  The ring is small enough to stay in the last-level cache, so the packers' (plain) stores
+    // and the DMA reads that follow mostly stay out of DRAM; a slot is reused once `copied` -- the number of
+    // packed jobs whose H2D copy has completed, advanced by the feeding thread -- has passed its last user.
+    void set_ring(unsigned char* base, size_t stride, int slots) {
+        ring_ = base;
+        stride_ = stride;
+        slots_ = slots;
+    }
+    unsigned char* slot_of(uint64_t seq) const { return ring_ + (size_t)(seq % (uint64_t)slots_) * stride_; }
+    std::atomic<uint64_t> copied{0};
+    std::atomic<uint64_t> pack_ns{0}, slot_wait_ns{0};  // summed over the worker threads (diagnostics)
+
+    // jobs must stay alive until every job is either packed or claimed raw; chunks go out in job order;
+    // job j is packed job number seq_base + j
+    void start(std::vector<PackJob>* jobs, uint64_t seq_base) {
         while (busy_.load(std::memory_order_acquire) != 0) std::this_thread::yield();  // stragglers of the previous run
+        seq_base_ = seq_base;
         chunks_.clear();
         first_chunk_.clear();
         for (size_t j = 0; j < jobs->size(); ++j) {
@@ -164,26 +178,37 @@ class HostPacker {
         return j;
     }
     bool packed(const PackJob& job) const { return job.remaining.load(std::memory_order_acquire) <= 0; }
-    bool help() { return work_one(); }  // the calling thread packs one chunk if any is left
+    bool help() { return work_one(false); }  // the calling thread packs one chunk if one can be started right away
 
-    static void pack_range(const gg_point* src, size_t n, unsigned char* dst, size_t i0, size_t i1) {
-        gg::pack_cloud_range(src, n, dst, i0, i1);
+    static void pack_range(const gg_point* src, size_t n, unsigned char* dst, size_t i0, size_t i1, bool cached = false) {
+        gg::pack_cloud_range(src, n, dst, i0, i1, cached);
     }
 
   private:
-    bool work_one() {
+    bool work_one(bool may_wait) {
         std::vector<PackJob>* jobs = jobs_;
         if (!jobs) return false;
         size_t c;
         {
             std::lock_guard<std::mutex> g(claim_mu_);
             if (next_ >= limit_) return false;
+            if (!may_wait && seq_base_ + (uint64_t)chunks_[next_].first >= copied.load(std::memory_order_acquire) + (uint64_t)slots_) return false;
             c = next_++;
         }
+        const uint64_t seq = seq_base_ + (uint64_t)chunks_[c].first;
+        const auto t0 = std::chrono::steady_clock::now();
+        while (seq >= copied.load(std::memory_order_acquire) + (uint64_t)slots_) {  // the slot's previous cloud is still on its way
+            if (stop_) return false;
+            std::this_thread::sleep_for(std::chrono::microseconds(20));
+        }
+        const auto t1 = std::chrono::steady_clock::now();
         PackJob& job = (*jobs)[chunks_[c].first];
         const size_t i0 = (size_t)chunks_[c].second * kChunk;
-        pack_range(job.src, job.n, job.dst, i0, std::min(job.n, i0 + kChunk));
+        pack_range(job.src, job.n, slot_of(seq), i0, std::min(job.n, i0 + kChunk), true);
         job.remaining.fetch_sub(1, std::memory_order_release);
+        const auto t2 = std::chrono::steady_clock::now();
+        slot_wait_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count(), std::memory_order_relaxed);
+        pack_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t2 - t1).count(), std::memory_order_relaxed);
         return true;
     }
     void loop() {
@@ -196,7 +221,7 @@ class HostPacker {
                 if (stop_) return;
                 busy_.fetch_add(1, std::memory_order_acq_rel);
             }
-            while (work_one()) {
+            while (work_one(true)) {
             }
             busy_.fetch_sub(1, std::memory_order_acq_rel);
         }
@@ -207,11 +232,15 @@ class HostPacker {
     std::vector<PackJob>* jobs_ = nullptr;
     std::vector<std::pair<int, int>> chunks_;
     std::vector<size_t> first_chunk_;
+    unsigned char* ring_ = nullptr;
+    size_t stride_ = 0;
+    int slots_ = 1;
+    uint64_t seq_base_ = 0;
     size_t next_ = 0, limit_ = 0;
     int raw_from_ = 0;
     std::atomic<int> busy_{0};
     uint64_t epoch_ = 0;
-    bool stop_ = false;
+    std::atomic<bool> stop_{false};
 };
 
 struct SlotState {
@@ -257,7 +286,10 @@ struct gg_handle_s {
     HostPacker* packer = nullptr;    // created on the first packed batch call
     // gg_filter_cloud_batch[_begin] alternates between two sets of input / label buffers ("parity"), so the
     // clouds of batch t+1 can be packed and copied while the kernels of batch t still read theirs
-    unsigned char* h_packed[2] = {};   // pinned staging, [n_slots][14 * pcap]
+    unsigned char* h_stage = nullptr;  // pinned staging ring of the packers, [pack_slots][14 * pcap] (HostPacker::set_ring)
+    int pack_slots = 32;               // GG_PACK_RING
+    std::vector<cudaEvent_t> slot_ev;  // [pack_slots] H2D of the slot's current cloud
+    uint64_t pack_issued = 0;          // packed jobs whose copy has been enqueued (HostPacker::copied counts the completed ones)
     unsigned char* in_packed[2] = {};  // device, same shape
     gg_point* in_raw[2] = {};          // device 32-byte records; [0] is the slots' own buffer (view.points)
     uint8_t* labels_buf[2] = {};       // [0] is the buffer the handle was created with
@@ -267,16 +299,19 @@ struct gg_handle_s {
     int host_pack = 1;               // GG_HOST_PACK=0 sends the 32-byte records as they are
     int launch_unit = 32;            // GG_LAUNCH_UNIT: scans per kernel launch set in gg_filter_cloud_batch
     int host_pack_mix = 1;           // GG_HOST_PACK=1 pins "pack everything"; default: pack and send raw side by side
-    cudaStream_t copy_in[8] = {}, copy_out = nullptr;  // H2D / D2H of gg_filter_cloud_batch, never behind kernels
+    cudaStream_t copy_in[10] = {}, copy_out = nullptr;  // [0, n_copy_in): packed clouds, then 2 for raw clouds;  // H2D / D2H of gg_filter_cloud_batch, never behind kernels
     int n_copy_in = 4;                                   // GG_COPY_STREAMS
     int main_help = 1;                                   // GG_MAIN_HELP
+    float4* detect_tab = nullptr;  // per-cell constants of the patch detection, rebuilt by gg_set_config
     bool inputs_busy = false;  // asynchronous work that reads or writes the slots' input buffers may be in flight
     std::vector<cudaEvent_t> batch_ev;                    // unit hand-over events of gg_filter_cloud_batch
     cudaEvent_t raw_ev[8] = {};      // throttle of the raw copies issued by the mixing loop
+    int raw_gate = 2;                // GG_RAW_GATE: no raw copies while this many packed clouds wait for the bus
     int raw_depth = 4;               // GG_RAW_DEPTH: raw copies in flight before the loop stops claiming more
     size_t last_raw = 0, last_packed = 0;  // scans sent raw / packed by the last batch call
     size_t last_raw_bytes = 0, last_packed_bytes = 0;
-    size_t last_feed_us = 0, last_total_us = 0;  // host time until the last cloud was enqueued / until everything was done
+    size_t last_feed_us = 0, last_total_us = 0;
+    size_t last_pack_us = 0, last_slot_wait_us = 0, last_idle_us = 0;  // worker-thread sums; feeder time with nothing to enqueue  // host time until the last cloud was enqueued / until everything was done
     EventProfiler* prof = nullptr;   // non-null while profiling is enabled
     double prof_ms[gg::K_NUM] = {};
     uint32_t prof_count[gg::K_NUM] = {};
@@ -541,6 +576,8 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
     float* expected = nullptr;
     GG_TRY(dev_alloc(h, &expected, N2));
     v.expected = expected;
+    GG_TRY(dev_alloc(h, &h->detect_tab, N2));
+    v.detect_tab = h->detect_tab;
     GG_TRY(dev_alloc(h, &v.points, S * P));
     GG_TRY(dev_alloc(h, &v.kz, S * P));
     GG_TRY(dev_alloc(h, &v.kz2, S * P));
@@ -702,6 +739,7 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
     if (const char* e = getenv("GG_LAUNCH_UNIT")) h->launch_unit = std::max(1, atoi(e));
     if (const char* e = getenv("GG_COPY_STREAMS")) h->n_copy_in = std::min(8, std::max(1, atoi(e)));
     if (const char* e = getenv("GG_MAIN_HELP")) h->main_help = atoi(e);
+    if (const char* e = getenv("GG_RAW_GATE")) h->raw_gate = std::max(1, atoi(e));
     if (const char* e = getenv("GG_RAW_DEPTH")) h->raw_depth = std::min(8, std::max(1, atoi(e)));
     if (const char* e = getenv("GG_HOST_PACK")) {
         h->host_pack = atoi(e) ? 1 : 0;
@@ -721,6 +759,9 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
     GG_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h->h_ring), sizeof(gg::SlotParams) * kRing * S, cudaHostAllocDefault));
     GG_TRY(dev_alloc(h, &h->d_ring, (size_t)kRing * S));
     for (int i = 0; i < kRing; ++i) GG_CUDA_TRY(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
+    h->launches += gg::launch_build_detect_table(v, h->detect_tab, h->streams[0]);
+    GG_CUDA_TRY(cudaGetLastError());
+    GG_CUDA_TRY(cudaStreamSynchronize(h->streams[0]));
 #undef GG_TRY
 #undef GG_CUDA_TRY
     *out = h;
@@ -734,14 +775,14 @@ int gg_destroy(gg_handle h) {
     delete h->prof;
     delete h->packer;
     if (h->d_raw) cudaFree(h->d_raw);
-    for (int e = 0; e < 2; ++e) {
-        if (h->h_packed[e]) cudaFreeHost(h->h_packed[e]);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    for (cudaEvent_t e : h->slot_ev) cudaEventDestroy(e);
+    for (int e = 0; e < 2; ++e)
         if (h->batch_done[e]) cudaEventDestroy(h->batch_done[e]);
-    }
     for (int e = 0; e < 8; ++e)
         if (h->raw_ev[e]) cudaEventDestroy(h->raw_ev[e]);
     for (cudaEvent_t e : h->batch_ev) cudaEventDestroy(e);
-    for (int e = 0; e < 8; ++e)
+    for (int e = 0; e < 10; ++e)
         if (h->copy_in[e]) cudaStreamDestroy(h->copy_in[e]);
     if (h->copy_out) cudaStreamDestroy(h->copy_out);
     for (void* p : h->dev_allocs) cudaFree(p);
@@ -770,8 +811,14 @@ int gg_spiral_schedule_info(gg_handle h, int* levels, int* visits, int* max_per_
 
 int gg_set_config(gg_handle h, const gg_config* cfg) {
     if (!h || !cfg) return fail(GG_E_ARG, "null argument");
+    GG_CUDA(cudaSetDevice(h->device));
+    int rc = gg_synchronize(h);  // kernels in flight keep the tables of the old configuration
+    if (rc) return rc;
     h->cfg = *cfg;
     gg::derive_constants(h->cfg, h->dimension_m, h->resolution, h->flags, h->view.k);  // by-value kernel argument: applies to the next launch
+    h->launches += gg::launch_build_detect_table(h->view, h->detect_tab, h->streams[0]);
+    GG_CUDA(cudaGetLastError());
+    GG_CUDA(cudaStreamSynchronize(h->streams[0]));
     return GG_OK;
 }
 
@@ -1099,18 +1146,21 @@ int batch_prepare(gg_handle h) {
     if (!h->copy_out) {
         for (int e = 0; e < 8; ++e) GG_CUDA(cudaEventCreateWithFlags(&h->raw_ev[e], cudaEventDisableTiming));
         for (int e = 0; e < 2; ++e) GG_CUDA(cudaEventCreateWithFlags(&h->batch_done[e], cudaEventDisableTiming));
-        for (int e = 0; e < h->n_copy_in; ++e) GG_CUDA(cudaStreamCreateWithFlags(&h->copy_in[e], cudaStreamNonBlocking));
+        for (int e = 0; e < h->n_copy_in + 2; ++e) GG_CUDA(cudaStreamCreateWithFlags(&h->copy_in[e], cudaStreamNonBlocking));
         GG_CUDA(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
         h->in_raw[0] = h->view.points;
         h->labels_buf[0] = h->view.labels;
     }
-    if (h->host_pack && !h->h_packed[0]) {
+    if (h->host_pack && !h->h_stage) {
         if ((rc = dev_alloc(h, &h->in_raw[1], (size_t)h->n_slots * h->pcap))) return rc;
         if ((rc = dev_alloc(h, &h->labels_buf[1], (size_t)h->n_slots * h->pcap))) return rc;
-        for (int e = 0; e < 2; ++e) {
-            GG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->h_packed[e]), (size_t)h->n_slots * 14 * h->pcap, cudaHostAllocDefault));
+        for (int e = 0; e < 2; ++e)
             if ((rc = dev_alloc(h, &h->in_packed[e], (size_t)h->n_slots * 14 * h->pcap))) return rc;
-        }
+        if (const char* e = getenv("GG_PACK_RING")) h->pack_slots = std::min(256, std::max(2, atoi(e)));
+        GG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->h_stage), (size_t)h->pack_slots * 14 * h->pcap, cudaHostAllocDefault));
+        h->slot_ev.resize(h->pack_slots);
+        for (cudaEvent_t& e : h->slot_ev) GG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->packer->set_ring(h->h_stage, 14 * h->pcap, h->pack_slots);
     }
     return GG_OK;
 }
@@ -1171,12 +1221,11 @@ int gg_filter_cloud_batch_begin(gg_handle h, int count, const gg_scan_desc* scan
         // stream of the slot) -> label read-back.  Kernels are enqueued for `launch_unit` delivered scans
         // of a stream group at a time, so that only the kernels of the last few scans run after the
         // transfers have ended.
-        unsigned char* const hpk = h->h_packed[par];
         unsigned char* const dpk = h->in_packed[par];
         gg_point* const draw = h->in_raw[par];
         uint8_t* const dlab = h->labels_buf[par];
         h->view.labels = dlab;  // what gg_download_labels / gg_get_output read after this batch
-        const int KC = h->n_copy_in;
+        const int KP = h->n_copy_in, KC = KP + 2;  // packed clouds rotate over the first KP copy streams, raw ones over the last 2
         std::vector<int> order;
         for (int g = 0; g < h->n_streams; ++g)
             for (int i = 0; i < count; ++i)
@@ -1186,7 +1235,6 @@ int gg_filter_cloud_batch_begin(gg_handle h, int count, const gg_scan_desc* scan
             const gg_scan_desc& d = scans[order[k]];
             jobs[k].src = points[order[k]];
             jobs[k].n = d.n_points;
-            jobs[k].dst = hpk + (size_t)d.slot * 14 * h->pcap;
         }
         if (h->inputs_busy) {  // earlier asynchronous calls may still use the slots' own input buffers
             for (int g = 0; g < h->n_streams; ++g) {
@@ -1247,15 +1295,27 @@ int gg_filter_cloud_batch_begin(gg_handle h, int count, const gg_scan_desc* scan
             pending[g].push_back(k);
             return (int)pending[g].size() >= h->launch_unit ? flush(g) : GG_OK;
         };
-        h->packer->start(&jobs);
+        const uint64_t seq_base = h->pack_issued;
+        auto poll_copies = [&] {  // staging slots whose cloud has reached the device go back to the packers, in order
+            uint64_t done = h->packer->copied.load(std::memory_order_relaxed);
+            while (done < h->pack_issued && cudaEventQuery(h->slot_ev[done % (uint64_t)h->pack_slots]) == cudaSuccess) ++done;
+            h->packer->copied.store(done, std::memory_order_release);
+        };
+        h->packer->pack_ns = 0;
+        h->packer->slot_wait_ns = 0;
+        uint64_t idle_ns = 0;
+        h->packer->start(&jobs, seq_base);
         int front = 0, back = count, raw_issued = 0, n_copies = 0;
         while (front < back) {
+            poll_copies();
             if (h->packer->packed(jobs[front])) {
                 const gg_scan_desc& d = scans[order[front]];
                 const size_t n_pad = (d.n_points + 7) & ~(size_t)7;
+                cudaStream_t cs = h->copy_in[n_copies++ % KP];
                 if (d.n_points)
-                    GG_CUDA(cudaMemcpyAsync(dpk + (size_t)d.slot * 14 * h->pcap, jobs[front].dst, 14 * n_pad, cudaMemcpyHostToDevice,
-                                            h->copy_in[n_copies++ % KC]));
+                    GG_CUDA(cudaMemcpyAsync(dpk + (size_t)d.slot * 14 * h->pcap, h->packer->slot_of(h->pack_issued), 14 * n_pad, cudaMemcpyHostToDevice, cs));
+                GG_CUDA(cudaEventRecord(h->slot_ev[h->pack_issued % (uint64_t)h->pack_slots], cs));
+                ++h->pack_issued;
                 sent_packed[front] = 1;
                 ++h->last_packed;
                 h->last_packed_bytes += 14 * n_pad;
@@ -1263,14 +1323,18 @@ int gg_filter_cloud_batch_begin(gg_handle h, int count, const gg_scan_desc* scan
                 ++front;
                 continue;
             }
-            const bool bus_free = h->host_pack_mix && (raw_issued < h->raw_depth || cudaEventQuery(h->raw_ev[raw_issued % h->raw_depth]) == cudaSuccess);
+            // A raw cloud costs 32 B/point of bus time, a packed one 14: raw copies are only worth it while the
+            // packed clouds do not queue up themselves (then the bus, not the packers, is what limits the batch).
+            const bool packed_backlog = h->pack_issued - h->packer->copied.load(std::memory_order_relaxed) >= (uint64_t)h->raw_gate;
+            const bool bus_free = h->host_pack_mix && !packed_backlog &&
+                                  (raw_issued < h->raw_depth || cudaEventQuery(h->raw_ev[raw_issued % h->raw_depth]) == cudaSuccess);
             int j = bus_free ? h->packer->claim_raw_from_back() : -1;
             if (j >= 0) {
                 const gg_scan_desc& d = scans[order[j]];
                 if (d.n_points)
                     GG_CUDA(cudaMemcpyAsync(draw + (size_t)d.slot * h->pcap, jobs[j].src, d.n_points * sizeof(gg_point), cudaMemcpyHostToDevice,
-                                            h->copy_in[n_copies % KC]));
-                GG_CUDA(cudaEventRecord(h->raw_ev[raw_issued % h->raw_depth], h->copy_in[n_copies++ % KC]));
+                                            h->copy_in[KP + (raw_issued & 1)]));
+                GG_CUDA(cudaEventRecord(h->raw_ev[raw_issued % h->raw_depth], h->copy_in[KP + (raw_issued & 1)]));
                 ++raw_issued;
                 ++h->last_raw;
                 h->last_raw_bytes += d.n_points * sizeof(gg_point);
@@ -1279,8 +1343,13 @@ int gg_filter_cloud_batch_begin(gg_handle h, int count, const gg_scan_desc* scan
                 continue;
             }
             // nothing to enqueue: with the raw queue full (or no mixing) this thread packs a chunk as well
+            const auto i0 = std::chrono::steady_clock::now();
             if ((h->host_pack_mix && (bus_free || !h->main_help)) || !h->packer->help()) std::this_thread::yield();
+            idle_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - i0).count();
         }
+        h->last_pack_us = h->packer->pack_ns.load() / 1000;
+        h->last_slot_wait_us = h->packer->slot_wait_ns.load() / 1000;
+        h->last_idle_us = idle_ns / 1000;
         for (int g = 0; g < h->n_streams; ++g)
             if ((rc = flush(g))) return rc;
         h->batch_parity ^= 1;
@@ -1362,21 +1431,24 @@ int gg_num_streams(gg_handle h) { return h ? h->n_streams : GG_E_ARG; }
 
 // host-only: the repacking of gg_filter_cloud_batch for one cloud (dst: 14 * ((n + 7) & ~7) bytes,
 // 32-byte aligned), chunked like the worker threads do it -- exported for the CPU tests
-int gg_host_pack_cloud(const gg_point* src, size_t n, unsigned char* dst) {
+static int pack_whole_cloud(const gg_point* src, size_t n, unsigned char* dst, bool cached) {
     if ((!src && n) || !dst) return GG_E_ARG;
     size_t i0 = 0;
     do {
         const size_t i1 = std::min(n, i0 + HostPacker::kChunk);
-        HostPacker::pack_range(src, n, dst, i0, i1);
+        HostPacker::pack_range(src, n, dst, i0, i1, cached);
         i0 = i1;
     } while (i0 < n);
     return GG_OK;
 }
+int gg_host_pack_cloud(const gg_point* src, size_t n, unsigned char* dst) { return pack_whole_cloud(src, n, dst, false); }
+// same with plain (cache-allocating) stores
+int gg_host_pack_cloud_cached(const gg_point* src, size_t n, unsigned char* dst) { return pack_whole_cloud(src, n, dst, true); }
 
 // number of host threads that repack clouds in gg_filter_cloud_batch (0: packing disabled or not used yet)
 int gg_host_pack_threads(gg_handle h) { return (h && h->host_pack && h->packer) ? h->packer->threads() + 1 : 0; }
 
-int gg_last_batch_transfer(gg_handle h, size_t info[6]) {
+int gg_last_batch_transfer(gg_handle h, size_t info[9]) {
     if (!h || !info) return fail(GG_E_ARG, "null argument");
     info[0] = h->last_packed;
     info[1] = h->last_raw;
@@ -1384,6 +1456,9 @@ int gg_last_batch_transfer(gg_handle h, size_t info[6]) {
     info[3] = h->last_raw_bytes;
     info[4] = h->last_feed_us;
     info[5] = h->last_total_us;
+    info[6] = h->last_pack_us;
+    info[7] = h->last_slot_wait_us;
+    info[8] = h->last_idle_us;
     return GG_OK;
 }
 

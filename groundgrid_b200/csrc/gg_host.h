@@ -11,7 +11,9 @@ void build_expected_points(int n, std::vector<float>& table);
 void derive_constants(const gg_config& c, double dimension_m, float resolution, unsigned flags, Const& k);
 void move_map(double res, double& px, double& py, double nx, double ny, int& shift_i, int& shift_j);
 void build_spiral_schedule(int n, std::vector<int>& level_start, std::vector<uint32_t>& visits);
-void pack_cloud_range(const gg_point* src, size_t n, unsigned char* dst, size_t i0, size_t i1);
+// cached: plain stores (destination meant to stay in the last-level cache until the DMA engine reads it)
+// instead of streaming stores
+void pack_cloud_range(const gg_point* src, size_t n, unsigned char* dst, size_t i0, size_t i1, bool cached = false);
 int usable_cpus();
 
 // Tables of the skewed-layout spiral kernel (k_spiral_skew), see gg_host.cpp:build_spiral_skew.
@@ -43,5 +45,6 @@ int gg_host_spiral_schedule(int n, int* level_start, int level_cap, uint32_t* vi
 int gg_host_spiral_records(int n, float resolution, int dist, uint32_t* recs, int rec_cap_words, int* max_recent);
 int gg_host_move_map(double res, double* pos_xy, double nx, double ny, int* shift_ij);
 int gg_host_pack_cloud(const gg_point* src, size_t n, unsigned char* dst);
+int gg_host_pack_cloud_cached(const gg_point* src, size_t n, unsigned char* dst);
 int gg_host_spiral_skew(int n, int* header, int* pattern, int* lane_begin, int* lane_end, int* cell_home, int* irr_level_start, uint32_t* irr_recs, int irr_cap_words);
 }

@@ -55,6 +55,7 @@ struct Const {
     double df_sq, mdf_sq, mdf10_sq, psc_sq;
     double occ_factor, occ_factor2, dec_factor;
     double lab_fac, lab_thres, lab_obs;
+    int decay_floor_ok;     // decay of a confidence <= 0.001f gives 0.001f again (checked on the host for dec_factor)
 };
 
 // Per-scan, per-slot parameters (changes every scan / pose update).
@@ -101,6 +102,7 @@ struct View {
     float* layers;        // [n_slots][n_layers][N2]
     int n_layers;
     const float* expected;  // [N2] expectedPoints table (GroundSegmentation.cpp:40-46)
+    const float4* detect_tab;  // [N2] per-cell constants of the patch detection (gg_kernels.cu:k_build_detect_table)
     gg_point* points;     // [n_slots][pcap]
     unsigned char* packed;  // [n_slots][14 * pcap] packed clouds (allocated on first use)
     uint2* kz;            // [n_slots][pcap] (sort key, z bits) per input point: key = cell index of kept points, N2 for everything else
@@ -156,6 +158,7 @@ struct Profiler {
 // ---- launchers (gg_kernels.cu); every function enqueues on `st` and returns the number of
 // kernel launches it issued (for gg_kernel_launches()). -----------------------------------
 int launch_init_map(const View& v, int slot, float z, cudaStream_t st);
+int launch_build_detect_table(const View& v, float4* tab, cudaStream_t st);
 int launch_roll(const View& v, const SlotParams* batch, int count, cudaStream_t st, Profiler* prof);
 int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int max_points, int stop_after, cudaStream_t st,
                          Profiler* prof);

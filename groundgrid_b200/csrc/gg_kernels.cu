@@ -481,13 +481,16 @@ constexpr int DT_R = DT_Y + 2 * DT_H;   // 12
 
 // confidence decay of interpolate_cell (:464): std::max(c - c / decrease_factor, 0.001) in fp64
 __device__ __forceinline__ float decay_confidence(const Const& k, float occ) {
+    // Confidences sit at the 0.001 floor in most of the map; from there (and below) the result is the floor
+    // again (host-checked for the configured factor, Const::decay_floor_ok), which skips the fp64 division.
+    if (k.decay_floor_ok && occ <= 0.001f) return 0.001f;
     const double o = (double)occ;
     const double dec = __dsub_rn(o, __ddiv_rn(o, k.dec_factor));
     return (float)((dec < 0.001) ? 0.001 : dec);
 }
 
 // Fused into k_detect: every cell is copied to its home slot(s) as soon as its final G, C are known.
-__device__ __forceinline__ void skew_store_cell(const View& v, const SlotParams& sp, int cell, int x, int y, float g, float c) {
+__device__ __forceinline__ void skew_store_cell(const View& v, const SlotParams& sp, int cell, int x, int y, float g, float c, bool far) {
     const Const& k = v.k;
     const int4 home = __ldg(reinterpret_cast<const int4*>(v.skew.cell_home) + cell);
     if (home.x < 0) return;
@@ -496,9 +499,7 @@ __device__ __forceinline__ void skew_store_cell(const View& v, const SlotParams&
         g = sp.base_z_f;
         c = 1.0f;
     }
-    // :463: beyond minDistSquared the visit stores the decayed confidence (:464)
-    const float fx = __fsub_rn((float)x, (float)cidx), fy = __fsub_rn((float)y, (float)cidx);
-    const bool far = __dmul_rn(__dadd_rn(__dmul_rn((double)fx, (double)fx), __dmul_rn((double)fy, (double)fy)), k.res_sq) > 12.0;
+    // :463: beyond minDistSquared (`far`, from the per-cell table) the visit stores the decayed confidence (:464)
     const float d1 = far ? decay_confidence(k, c) : -1.0f;
     float2* SK = v.skew.sk + (size_t)sp.slot * v.skew.slots;
     float* SD = v.skew.sd + (size_t)sp.slot * v.skew.slots;
@@ -513,22 +514,48 @@ __device__ __forceinline__ void skew_store_cell(const View& v, const SlotParams&
     if (home.w >= 0) SK[home.w] = gc;
 }
 
-template <int S>
-__device__ __forceinline__ void detect_patch(const Const& k, const float (*sP)[DT_W], const float (*sV)[DT_W], const float (*sM)[DT_W],
-                                             int li, int lj, float sqdist, float e, float* Gp, float* Cp) {
-    constexpr int H = S / 2;
-    const int r0 = li - H, c0 = lj - H;  // block origin in the shared tile (row index = i, col = j)
-    const float psum = TreeSum<0, S * S>::run([&](int q) { return sP[c0 + q / S][r0 + q % S]; });
-    const float oc = *Cp, og = *Gp;
+// Per-cell quantities of detect_ground_patches that depend only on the grid and the configuration, computed
+// once (gg_create / gg_set_config) with the very operations of the per-scan code they replace:
+//   x: max(3, floor(threshold * S * expectedPoints))  (:364; integer valued, exact in float, capped at 2^24)
+//   y: variance threshold (:369)      z: expectedPoints      w: flags
+constexpr int DTF_S5 = 1, DTF_FAR = 2, DTF_INNER = 4;
 
-    // early skipping of (almost) empty areas, :364
-    const double need = floor(__dmul_rn(__dmul_rn(k.gp_thresh, (double)S), (double)e));
-    if ((double)psum < ((need < 3.0) ? 3.0 : need)) return;
-
-    // variance threshold, :369
+__global__ void k_build_detect_table(View v, float4* __restrict__ tab) {
+    const Const& k = v.k;
+    const int N = k.N;
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= k.N2) return;
+    const int i = cell % N, j = cell / N;
+    const double di = __dsub_rn((double)i, (double)N / 2.0), dj = __dsub_rn((double)j, (double)N / 2.0);
+    const float sqdist = (float)__dmul_rn(__dadd_rn(__dmul_rn(di, di), __dmul_rn(dj, dj)), k.res_sq);  // :332,356
+    const float e = v.expected[cell];
+    int flags = 0;
+    if (!((double)sqdist <= k.psc_sq)) flags |= DTF_S5;
+    if (!(i < 2 || j < 2 || i >= N - 2 || j >= N - 2)) flags |= DTF_INNER;  // union of the four sections, :325-328
+    const int cidx = N / 2 - 1;
+    const float fx = __fsub_rn((float)i, (float)cidx), fy = __fsub_rn((float)j, (float)cidx);
+    if (__dmul_rn(__dadd_rn(__dmul_rn((double)fx, (double)fx), __dmul_rn((double)fy, (double)fy)), k.res_sq) > 12.0) flags |= DTF_FAR;  // :463
+    const double S = (flags & DTF_S5) ? 5.0 : 3.0;
+    double need = floor(__dmul_rn(__dmul_rn(k.gp_thresh, S), (double)e));
+    need = (need < 3.0) ? 3.0 : need;                 // NaN -> NaN: the comparison below stays false, as in the reference
+    if (need > 16777216.0) need = 16777216.0;         // patch sums are counts far below 2^24
     const double a = __dmul_rn((double)sqdist, k.df_sq);
     const double m = (a < k.mdf_sq) ? k.mdf_sq : a;
     const float vt = (float)((k.mdf10_sq < m) ? k.mdf10_sq : m);
+    tab[cell] = make_float4((float)need, vt, e, __int_as_float(flags));
+}
+
+// returns true when (g, c) changed
+template <int S>
+__device__ __forceinline__ bool detect_patch(const Const& k, const float (*sP)[DT_W], const float (*sV)[DT_W], const float (*sM)[DT_W],
+                                             int li, int lj, float need, float vt, float e, float& g, float& c) {
+    constexpr int H = S / 2;
+    const int r0 = li - H, c0 = lj - H;  // block origin in the shared tile (row index = i, col = j)
+    const float psum = TreeSum<0, S * S>::run([&](int q) { return sP[c0 + q / S][r0 + q % S]; });
+    const float oc = c, og = g;
+
+    // early skipping of (almost) empty areas, :364 (both sides integer valued: the float compare is the double one)
+    if (psum < need) return false;
 
     const float variance = sV[lj][li];
     float localmin = sM[c0][r0];
@@ -546,7 +573,7 @@ __device__ __forceinline__ void detect_patch(const Const& k, const float (*sP)[D
     const float groundDiff = (gd < 1.0f) ? 1.0f : gd;  // std::max(gd, 1.0f)
 
     // do not update known high confidence estimations upward, :379
-    if ((double)oc > 0.5 && (double)groundlevel >= __dadd_rn((double)og, k.outlier_tol)) return;
+    if ((double)oc > 0.5 && (double)groundlevel >= __dadd_rn((double)og, k.outlier_tol)) return false;
 
     if ((double)vt > __dmul_rn((double)maxVar, (double)maxVar) && maxVar > 0.0f &&
         (double)psum > __dmul_rn((double)__fmul_rn(__fmul_rn(groundDiff, e), (float)S), k.gp_thresh)) {
@@ -554,17 +581,22 @@ __device__ __forceinline__ void detect_patch(const Const& k, const float (*sP)[D
         const float nc = (float)((1.0 < ncd) ? 1.0 : ncd);  // std::min(ncd, 1.0)
         const float num = __fadd_rn(__fmul_rn(groundlevel, nc), __fmul_rn(__fmul_rn(oc, og), 2.0f));
         const float den = __fadd_rn(nc, __fmul_rn(oc, 2.0f));
-        *Gp = __fdiv_rn(num, den);
+        g = __fdiv_rn(num, den);
         const double cd = __ddiv_rn(__dadd_rn(__ddiv_rn((double)psum, k.occ_factor2), (double)oc), 2.0);
-        *Cp = (float)((1.0 < cd) ? 1.0 : cd);
-    } else if (localmin < og) {
-        *Gp = localmin;
-        const float t = __fadd_rn(oc, 0.1f);
-        *Cp = (0.5f < t) ? 0.5f : t;  // std::min(oc + 0.1f, 0.5f)
+        c = (float)((1.0 < cd) ? 1.0 : cd);
+        return true;
     }
+    if (localmin < og) {
+        g = localmin;
+        const float t = __fadd_rn(oc, 0.1f);
+        c = (0.5f < t) ? 0.5f : t;  // std::min(oc + 0.1f, 0.5f)
+        return true;
+    }
+    return false;
 }
 
-__global__ void __launch_bounds__(DT_X* DT_Y) k_detect(View v, const SlotParams* __restrict__ batch) {
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(DT_X* DT_Y, MIN_BLOCKS) k_detect(View v, const SlotParams* __restrict__ batch) {
     __shared__ float sP[DT_R][DT_W], sV[DT_R][DT_W], sM[DT_R][DT_W];
     const SlotParams& sp = batch[blockIdx.z];
     const Const& k = v.k;
@@ -574,43 +606,68 @@ __global__ void __launch_bounds__(DT_X* DT_Y) k_detect(View v, const SlotParams*
     const float* V = v.layer(sp.slot, L_VARIANCE);
     const float* M = v.layer(sp.slot, L_MINH);
     const int tid = threadIdx.y * DT_X + threadIdx.x;
-    for (int t = tid; t < DT_R * DT_W; t += DT_X * DT_Y) {
+    // tile + halo: all global loads of a thread are issued before the first shared store
+    constexpr int PER_THREAD = (DT_R * DT_W + DT_X * DT_Y - 1) / (DT_X * DT_Y);
+    float tp[PER_THREAD], tv[PER_THREAD], tm[PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < PER_THREAD; ++u) {
+        const int t = tid + u * DT_X * DT_Y;
         const int lj = t / DT_W, li = t % DT_W;
         const int gi = i0 - DT_H + li, gj = j0 - DT_H + lj;
-        const bool in = gi >= 0 && gi < N && gj >= 0 && gj < N;
+        const bool in = t < DT_R * DT_W && gi >= 0 && gi < N && gj >= 0 && gj < N;
         const int g = gi + gj * N;
-        sP[lj][li] = in ? P[g] : 0.0f;
-        sV[lj][li] = in ? V[g] : 0.0f;
-        sM[lj][li] = in ? M[g] : FLT_MAX;
+        tp[u] = in ? P[g] : 0.0f;
+        tv[u] = in ? V[g] : 0.0f;
+        tm[u] = in ? M[g] : FLT_MAX;
+    }
+    const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
+    const bool live = i < N && j < N;
+    const int cell = i + j * N;
+    float g = 0.0f, c = 0.0f;
+    float4 tb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (live) {
+        g = v.layer(sp.slot, L_GROUND)[cell];
+        c = v.layer(sp.slot, L_GROUNDPATCH)[cell];
+        tb = __ldg(v.detect_tab + cell);
+    }
+#pragma unroll
+    for (int u = 0; u < PER_THREAD; ++u) {
+        const int t = tid + u * DT_X * DT_Y;
+        if (t < DT_R * DT_W) {
+            sP[t / DT_W][t % DT_W] = tp[u];
+            sV[t / DT_W][t % DT_W] = tv[u];
+            sM[t / DT_W][t % DT_W] = tm[u];
+        }
     }
     __syncthreads();
-    const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
-    if (i >= N || j >= N) return;
-    float* Gp = v.layer(sp.slot, L_GROUND) + i + j * N;
-    float* Cp = v.layer(sp.slot, L_GROUNDPATCH) + i + j * N;
-    if (!(i < 2 || j < 2 || i >= N - 2 || j >= N - 2)) {  // union of the four sections, :325-328
-        const double di = __dsub_rn((double)i, (double)N / 2.0), dj = __dsub_rn((double)j, (double)N / 2.0);
-        const float sqdist = (float)__dmul_rn(__dadd_rn(__dmul_rn(di, di), __dmul_rn(dj, dj)), k.res_sq);  // :332,356
-        const float e = v.expected[i + j * N];
+    if (!live) return;
+    const int flags = __float_as_int(tb.w);
+    if (flags & DTF_INNER) {
         const int li = threadIdx.x + DT_H, lj = threadIdx.y + DT_H;
-        if ((double)sqdist <= k.psc_sq)
-            detect_patch<3>(k, sP, sV, sM, li, lj, sqdist, e, Gp, Cp);
-        else
-            detect_patch<5>(k, sP, sV, sM, li, lj, sqdist, e, Gp, Cp);
+        const bool changed = (flags & DTF_S5) ? detect_patch<5>(k, sP, sV, sM, li, lj, tb.x, tb.y, tb.z, g, c)
+                                              : detect_patch<3>(k, sP, sV, sM, li, lj, tb.x, tb.y, tb.z, g, c);
+        if (changed) {
+            v.layer(sp.slot, L_GROUND)[cell] = g;
+            v.layer(sp.slot, L_GROUNDPATCH)[cell] = c;
+        }
     }
     if (v.skew.sk) {
-        skew_store_cell(v, sp, i + j * N, i, j, *Gp, *Cp);
+        skew_store_cell(v, sp, cell, i, j, g, c, (flags & DTF_FAR) != 0);
     } else if (v.spiral_recs) {
         // Decayed confidence for the spiral sweep, taken off its sequential critical path: the
         // confidence of a cell only changes at its own visit(s), so decay(C) after patch
         // detection is exactly what the (first) visit will store; ring corners (i == j) are
         // visited twice and need the second decay as well.
-        const float cfin = *Cp;
-        const float d1 = decay_confidence(k, cfin);
+        const float d1 = decay_confidence(k, c);
         float* D1 = v.roll_scratch + (size_t)sp.slot * 2 * k.N2;
-        D1[i + j * N] = d1;
-        if (i == j) D1[k.N2 + i + j * N] = decay_confidence(k, d1);
+        D1[cell] = d1;
+        if (i == j) D1[k.N2 + cell] = decay_confidence(k, d1);
     }
+}
+
+int launch_build_detect_table(const View& v, float4* tab, cudaStream_t st) {
+    k_build_detect_table<<<(v.k.N2 + 255) / 256, 256, 0, st>>>(v, tab);
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1306,7 +1363,6 @@ int launch_roll(const View& v, const SlotParams* batch, int count, cudaStream_t 
 int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int max_points, int stop_after, cudaStream_t st,
                          Profiler* prof) {
     int launches = 0;
-    const int N2 = v.k.N2;
     const int pblocks = max(1, cdiv(max_points, 256));
     const int nb = max(1, cdiv(max_points, SORT_TILE));
 
@@ -1330,7 +1386,11 @@ int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int 
     ++launches;
     if (stop_after == 1) return launches;
 
-    GG_LAUNCH(K_DETECT, k_detect<<<dim3(cdiv(v.k.N, DT_X), cdiv(v.k.N, DT_Y), count), dim3(DT_X, DT_Y), 0, st>>>(v, batch));
+    static const int detect_occ = getenv("GG_DETECT_OCC") ? atoi(getenv("GG_DETECT_OCC")) : 4;
+    if (detect_occ >= 4)
+        GG_LAUNCH(K_DETECT, k_detect<4><<<dim3(cdiv(v.k.N, DT_X), cdiv(v.k.N, DT_Y), count), dim3(DT_X, DT_Y), 0, st>>>(v, batch));
+    else
+        GG_LAUNCH(K_DETECT, k_detect<3><<<dim3(cdiv(v.k.N, DT_X), cdiv(v.k.N, DT_Y), count), dim3(DT_X, DT_Y), 0, st>>>(v, batch));
     ++launches;
     if (stop_after == 2) return launches;
 

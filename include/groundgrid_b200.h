@@ -237,8 +237,11 @@ int gg_num_streams(gg_handle h);
 int gg_host_pack_threads(gg_handle h);
 /* How the last gg_filter_cloud_batch call moved its clouds: info[0] scans repacked on the host,
  * info[1] scans sent as 32-byte records, info[2] / info[3] the H2D bytes of either kind,
- * info[4] host microseconds until the last cloud was enqueued, info[5] until the call returned. */
-int gg_last_batch_transfer(gg_handle h, size_t info[6]);
+ * info[4] host microseconds until the last cloud was enqueued, info[5] until the call returned
+ * (synchronous call only), info[6] / info[7] microseconds the packer threads spent packing / waiting
+ * for a staging slot (summed over threads), info[8] microseconds the calling thread had nothing to
+ * enqueue. */
+int gg_last_batch_transfer(gg_handle h, size_t info[9]);
 int gg_fork_streams(gg_handle h);
 int gg_join_streams(gg_handle h);
 
