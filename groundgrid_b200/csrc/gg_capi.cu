@@ -643,25 +643,35 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
         // time-sharing of lane threads: the smallest M (multiple of 32) such that ring k + M of a side
         // starts (prefetch window included) only after ring k has finished
         // (only when one thread per lane does not fit a CTA: measured, a dedicated thread per lane is faster)
-        int M = 32, phases = 1;
+        // Two thread layouts of the same schedule.  "Latency": one thread per lane whenever that fits a CTA (measured:
+        // fastest for a single scan).  "Throughput": the smallest M, so that the CTA is small and two or three scans
+        // share an SM (measured: +4 % on batches).  GG_SPIRAL_M raises the throughput layout's M (0: same as latency).
+        int M = 32, phases = 1, M_thr = 32, phases_thr = 1;
         if (sk.ok) {
             const int kGap = 2 * 8 + 4;  // 2 * PF_FAR of k_spiral_skew + slack
-            if (4 * sk.KP + 64 <= 1024) M = sk.KP;
-            for (; M < sk.KP; M += 32) {
-                bool fits = true;
-                for (int sd = 0; sd < 4 && fits; ++sd)
-                    for (int c0 = 0; c0 + M < sk.KP && fits; ++c0) {
-                        const int a = sd * sk.KP + c0, b2 = a + M;
-                        if (sk.lane_begin[a] < sk.lane_end[a] && sk.lane_begin[b2] < sk.lane_end[b2] &&
-                            sk.lane_end[a] + kGap > sk.lane_begin[b2])
-                            fits = false;
-                    }
-                if (fits) break;
-            }
-            M = std::min(M, sk.KP);
+            auto smallest_fitting = [&](int m0) {
+                int m = m0;
+                for (; m < sk.KP; m += 32) {
+                    bool fits = true;
+                    for (int sd = 0; sd < 4 && fits; ++sd)
+                        for (int c0 = 0; c0 + m < sk.KP && fits; ++c0) {
+                            const int a = sd * sk.KP + c0, b2 = a + m;
+                            if (sk.lane_begin[a] < sk.lane_end[a] && sk.lane_begin[b2] < sk.lane_end[b2] &&
+                                sk.lane_end[a] + kGap > sk.lane_begin[b2])
+                                fits = false;
+                        }
+                    if (fits) break;
+                }
+                return std::min(m, sk.KP);
+            };
+            M = (4 * sk.KP + 64 <= 1024) ? sk.KP : smallest_fitting(32);
             phases = (sk.KP + M - 1) / M;
+            int m0 = 32;
+            if (const char* e = getenv("GG_SPIRAL_M")) m0 = atoi(e) / 32 * 32;
+            M_thr = m0 <= 0 ? M : smallest_fitting(std::max(32, m0));
+            phases_thr = (sk.KP + M_thr - 1) / M_thr;
             // one CTA: lane threads + the two irregular warps (one thread per (visit, neighbour))
-            if (4 * M + 64 > 1024 || sk.max_irr_per_level * 9 > 64) sk.ok = false;
+            if (4 * M + 64 > 1024 || 4 * M_thr + 64 > 1024 || sk.max_irr_per_level * 9 > 64) sk.ok = false;
         }
         if (sk.ok) {
             // re-layout of the irregular records: one dense block per level (see SkewView)
@@ -686,28 +696,39 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
                     hd[2] = w[13];
                     hd[3] = w[14];
                 }
-            std::vector<int> ph_b((size_t)phases * 4 * M, 0), ph_e((size_t)phases * 4 * M, 0), ph_c((size_t)phases * 4 * M, 0);
-            for (int ph = 0; ph < phases; ++ph)
-                for (int sd = 0; sd < 4; ++sd)
-                    for (int m = 0; m < M; ++m) {
-                        const int col = ph * M + m;
-                        if (col >= sk.KP) continue;
-                        const size_t dst = ((size_t)ph * 4 + sd) * M + m;
-                        ph_b[dst] = sk.lane_begin[sd * sk.KP + col];
-                        ph_e[dst] = sk.lane_end[sd * sk.KP + col];
-                        ph_c[dst] = sk.lane_cell0[sd * sk.KP + col];
-                    }
-            int *d_home = nullptr, *d_lb = nullptr, *d_le = nullptr, *d_lc = nullptr;
+            // [phase][side * M + m] tables of a layout
+            auto upload_phases = [&](int m_, int phases_, const int** d_b, const int** d_e, const int** d_c) -> int {
+                std::vector<int> ph_b((size_t)phases_ * 4 * m_, 0), ph_e((size_t)phases_ * 4 * m_, 0), ph_c((size_t)phases_ * 4 * m_, 0);
+                for (int ph = 0; ph < phases_; ++ph)
+                    for (int sd = 0; sd < 4; ++sd)
+                        for (int m = 0; m < m_; ++m) {
+                            const int col = ph * m_ + m;
+                            if (col >= sk.KP) continue;
+                            const size_t dst = ((size_t)ph * 4 + sd) * m_ + m;
+                            ph_b[dst] = sk.lane_begin[sd * sk.KP + col];
+                            ph_e[dst] = sk.lane_end[sd * sk.KP + col];
+                            ph_c[dst] = sk.lane_cell0[sd * sk.KP + col];
+                        }
+                int *d_lb = nullptr, *d_le = nullptr, *d_lc = nullptr;
+                int rc2;
+                if ((rc2 = dev_alloc(h, &d_lb, ph_b.size())) || (rc2 = dev_alloc(h, &d_le, ph_e.size())) || (rc2 = dev_alloc(h, &d_lc, ph_c.size())))
+                    return rc2;
+                if (cudaMemcpy(d_lb, ph_b.data(), ph_b.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+                    cudaMemcpy(d_le, ph_e.data(), ph_e.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+                    cudaMemcpy(d_lc, ph_c.data(), ph_c.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
+                    return fail(GG_E_CUDA, "upload of the spiral phase tables failed");
+                *d_b = d_lb;
+                *d_e = d_le;
+                *d_c = d_lc;
+                return GG_OK;
+            };
+            GG_TRY(upload_phases(M, phases, &v.skew.ph_begin, &v.skew.ph_end, &v.skew.ph_cell0));
+            GG_TRY(upload_phases(M_thr, phases_thr, &v.skew.thr_ph_begin, &v.skew.thr_ph_end, &v.skew.thr_ph_cell0));
+            int* d_home = nullptr;
             uint32_t* d_irr = nullptr;
             GG_TRY(dev_alloc(h, &d_home, sk.cell_home.size()));
-            GG_TRY(dev_alloc(h, &d_lb, ph_b.size()));
-            GG_TRY(dev_alloc(h, &d_le, ph_e.size()));
-            GG_TRY(dev_alloc(h, &d_lc, ph_c.size()));
             GG_TRY(dev_alloc(h, &d_irr, blocks.size() + 16));
             GG_CUDA_TRY(cudaMemcpy(d_home, sk.cell_home.data(), sk.cell_home.size() * sizeof(int), cudaMemcpyHostToDevice));
-            GG_CUDA_TRY(cudaMemcpy(d_lb, ph_b.data(), ph_b.size() * sizeof(int), cudaMemcpyHostToDevice));
-            GG_CUDA_TRY(cudaMemcpy(d_le, ph_e.data(), ph_e.size() * sizeof(int), cudaMemcpyHostToDevice));
-            GG_CUDA_TRY(cudaMemcpy(d_lc, ph_c.data(), ph_c.size() * sizeof(int), cudaMemcpyHostToDevice));
             GG_CUDA_TRY(cudaMemcpy(d_irr, blocks.data(), blocks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
             float2* d_sk = nullptr;
             float* d_sd = nullptr;
@@ -719,11 +740,10 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
             v.skew.sd = d_sd;
             v.skew.slots = sk.slots;
             v.skew.cell_home = d_home;
-            v.skew.ph_begin = d_lb;
-            v.skew.ph_end = d_le;
-            v.skew.ph_cell0 = d_lc;
             v.skew.M = M;
             v.skew.phases = phases;
+            v.skew.thr_M = M_thr;
+            v.skew.thr_phases = phases_thr;
             v.skew.irr_blocks = reinterpret_cast<const uint4*>(d_irr);
             v.skew.irr_max = irr_max;
             v.skew.irr_chunks = irr_words / 4;

@@ -86,6 +86,12 @@ struct SkewView {
     const int* ph_end;
     const int* ph_cell0;    // cell (x + y * N) of the first regular visit
     int M, phases;
+    // second layout of the same tables with the smallest possible M (small CTAs: several scans per SM); the
+    // launcher swaps it in for batches, the first one serves single scans (lowest latency)
+    const int* thr_ph_begin;
+    const int* thr_ph_end;
+    const int* thr_ph_cell0;
+    int thr_M, thr_phases;
     // irregular visits, one fixed-size block per level (irr_chunks x uint4):
     //   words [ (v * 9 + q) * 2 + {0, 1} ] = slot of neighbour q of visit v, producer lane if it was
     //                                        written one level ago (else 0xffffffff)

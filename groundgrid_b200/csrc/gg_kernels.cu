@@ -1104,8 +1104,8 @@ __device__ __forceinline__ void skew_irregular_thread(const View& v, const SlotP
     }
 }
 
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT) k_spiral_skew(View v, const SlotParams* __restrict__ batch) {
+template <int MAXT, int MIN_CTAS = 1>
+__global__ void __launch_bounds__(MAXT, MIN_CTAS) k_spiral_skew(View v, const SlotParams* __restrict__ batch) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const SkewView& w = v.skew;
     // [ring: SKEW_RING levels x irr_chunks uint4][xch: 2 x lanes float2][nb: irr_max*9 float2][dd: irr_max float]
@@ -1395,13 +1395,28 @@ int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int 
     if (stop_after == 2) return launches;
 
     if (v.skew.sk) {
-        const int threads = 4 * v.skew.M + SKEW_IRR_THREADS;
+        // batches run the small-CTA layout (two or three scans share an SM and leave room for the other streams'
+        // kernels); a few scans alone get one thread per lane.  GG_SPIRAL_SHARE_MIN: smallest batch that shares.
+        static const int share_min = getenv("GG_SPIRAL_SHARE_MIN") ? atoi(getenv("GG_SPIRAL_SHARE_MIN")) : 9;
+        View vs = v;
+        if (count >= share_min) {
+            vs.skew.M = v.skew.thr_M;
+            vs.skew.phases = v.skew.thr_phases;
+            vs.skew.ph_begin = v.skew.thr_ph_begin;
+            vs.skew.ph_end = v.skew.thr_ph_end;
+            vs.skew.ph_cell0 = v.skew.thr_ph_cell0;
+        }
+        const int threads = 4 * vs.skew.M + SKEW_IRR_THREADS;
         const size_t shm = (size_t)SKEW_RING * v.skew.irr_chunks * sizeof(uint4) + (size_t)2 * v.skew.lanes * sizeof(float2) +
                            (size_t)v.skew.irr_max * 9 * sizeof(float2) + (size_t)v.skew.irr_max * sizeof(float) + 16;
-        if (threads <= 768)
-            GG_LAUNCH(K_SPIRAL, k_spiral_skew<768><<<count, threads, shm, st>>>(v, batch));
+        if (threads <= 320)       // time-shared lane threads (GG_SPIRAL_M): several scans share an SM
+            GG_LAUNCH(K_SPIRAL, (k_spiral_skew<320, 3><<<count, threads, shm, st>>>(vs, batch)));
+        else if (threads <= 448)
+            GG_LAUNCH(K_SPIRAL, (k_spiral_skew<448, 2><<<count, threads, shm, st>>>(vs, batch)));
+        else if (threads <= 768)
+            GG_LAUNCH(K_SPIRAL, k_spiral_skew<768><<<count, threads, shm, st>>>(vs, batch));
         else
-            GG_LAUNCH(K_SPIRAL, k_spiral_skew<1024><<<count, threads, shm, st>>>(v, batch));
+            GG_LAUNCH(K_SPIRAL, k_spiral_skew<1024><<<count, threads, shm, st>>>(vs, batch));
     } else if (v.spiral_recs) {
         const size_t shm = (size_t)((v.levels + 4) & ~3) * sizeof(int) + (size_t)(v.spiral_dist + 1) * v.spiral_threads * sizeof(float2);
 #define GG_SPIRAL_CASE(T, D)                                                                      \

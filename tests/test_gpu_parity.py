@@ -309,6 +309,36 @@ def test_batched_slots_match_single_and_are_deterministic():
         assert np.array_equal(g2.layer("ground", slot=b), g.layer("ground", slot=b))
 
 
+@pytest.mark.parametrize("dim,res", [(33.0, 0.33), (99.0, 0.33), (120.0, 0.33)])
+def test_batch_of_ten_uses_the_shared_sm_spiral_layout(dim, res):
+    """Launches of >= 9 scans run the spiral with time-shared lane threads (small CTAs, several scans per SM);
+    fewer scans get one thread per lane.  Both must reproduce the sequential sweep bit for bit."""
+    import torch
+
+    B = 10
+    g = capi.GroundGridB200(dim, res, n_slots=B, max_points=131072, full_layers=False)
+    scans = [synth.scan_64(synth.make_scene(seed=700 + b), ego_xy=(0.05 * b, 0.0), seed=700 + b) for b in range(B)]
+    hp = [torch.from_numpy(np.ascontiguousarray(p).view(np.uint8).copy()).pin_memory() for p, _ in scans]
+    hl = [torch.zeros(len(p), dtype=torch.uint8).pin_memory() for p, _ in scans]
+    for b in range(B):
+        g.init_map(0.05 * b, 0.0, 0.0, slot=b)
+    got = []
+    for rep in range(2):
+        descs = g.make_descs(list(range(B)), [len(p) for p, _ in scans], [o for _, o in scans], [0.0] * B)
+        g.filter_cloud_batch_ptrs(descs, [t.data_ptr() for t in hp], [t.data_ptr() for t in hl])
+        got.append([t.numpy().copy() for t in hl])
+    for b in range(B):
+        o = Oracle(dim, res)
+        o.init_map(0.05 * b, 0.0, 0.0)
+        for rep in range(2):
+            want, _, _ = o.filter_cloud(scans[b][0], scans[b][1], 0.0, threads=1)
+            assert np.array_equal(got[rep][b], want), f"slot {b} rep {rep}"
+        for name in ("ground", "groundpatch"):
+            r = diff_report(name, g.layer(name, slot=b), o.layer(name))
+            assert r is None, f"slot {b}: {r}"
+    g.close()
+
+
 @pytest.mark.parametrize("unit", ["2", "32"])
 def test_overlapped_batches_begin_wait(monkeypatch, unit):
     """gg_filter_cloud_batch_begin/_wait: the clouds of step t+1 are packed and copied while the kernels of
