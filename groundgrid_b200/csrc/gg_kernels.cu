@@ -602,41 +602,46 @@ __global__ void __launch_bounds__(DT_X* DT_Y, MIN_BLOCKS) k_detect(View v, const
     const Const& k = v.k;
     const int N = k.N;
     const int i0 = blockIdx.x * DT_X, j0 = blockIdx.y * DT_Y;
-    const float* P = v.layer(sp.slot, L_COUNT);
-    const float* V = v.layer(sp.slot, L_VARIANCE);
-    const float* M = v.layer(sp.slot, L_MINH);
-    const int tid = threadIdx.y * DT_X + threadIdx.x;
-    // tile + halo: all global loads of a thread are issued before the first shared store
-    constexpr int PER_THREAD = (DT_R * DT_W + DT_X * DT_Y - 1) / (DT_X * DT_Y);
-    float tp[PER_THREAD], tv[PER_THREAD], tm[PER_THREAD];
+    // one 64-bit base per scan, 32-bit offsets below it (all layers of a slot span far less than 2^31 floats)
+    float* const L0 = v.layer(sp.slot, 0);
+    const int N2 = k.N2;
+    const float* P = L0 + L_COUNT * N2;
+    const float* V = L0 + L_VARIANCE * N2;
+    const float* M = L0 + L_MINH * N2;
+    // tile + halo (36 x 12): a thread fetches column li = tx of rows ty and ty + 8 (ty < 4) and, for tx < 4, the four
+    // extra halo columns 32 + tx of the same rows -- fixed positions, no div/mod; all global loads are issued before
+    // the first shared store
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    float tp[4], tv[4], tm[4];
 #pragma unroll
-    for (int u = 0; u < PER_THREAD; ++u) {
-        const int t = tid + u * DT_X * DT_Y;
-        const int lj = t / DT_W, li = t % DT_W;
+    for (int u = 0; u < 4; ++u) {
+        const int li = (u & 1) ? DT_X + tx : tx, lj = (u & 2) ? ty + DT_Y : ty;
+        const bool mine = ((u & 1) == 0 || tx < 2 * DT_H) && ((u & 2) == 0 || ty < 2 * DT_H);
         const int gi = i0 - DT_H + li, gj = j0 - DT_H + lj;
-        const bool in = t < DT_R * DT_W && gi >= 0 && gi < N && gj >= 0 && gj < N;
+        const bool in = mine && gi >= 0 && gi < N && gj >= 0 && gj < N;
         const int g = gi + gj * N;
         tp[u] = in ? P[g] : 0.0f;
         tv[u] = in ? V[g] : 0.0f;
         tm[u] = in ? M[g] : FLT_MAX;
     }
-    const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
+    const int i = i0 + tx, j = j0 + ty;
     const bool live = i < N && j < N;
     const int cell = i + j * N;
     float g = 0.0f, c = 0.0f;
     float4 tb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (live) {
-        g = v.layer(sp.slot, L_GROUND)[cell];
-        c = v.layer(sp.slot, L_GROUNDPATCH)[cell];
+        g = L0[L_GROUND * N2 + cell];
+        c = L0[L_GROUNDPATCH * N2 + cell];
         tb = __ldg(v.detect_tab + cell);
     }
 #pragma unroll
-    for (int u = 0; u < PER_THREAD; ++u) {
-        const int t = tid + u * DT_X * DT_Y;
-        if (t < DT_R * DT_W) {
-            sP[t / DT_W][t % DT_W] = tp[u];
-            sV[t / DT_W][t % DT_W] = tv[u];
-            sM[t / DT_W][t % DT_W] = tm[u];
+    for (int u = 0; u < 4; ++u) {
+        const int li = (u & 1) ? DT_X + tx : tx, lj = (u & 2) ? ty + DT_Y : ty;
+        const bool mine = ((u & 1) == 0 || tx < 2 * DT_H) && ((u & 2) == 0 || ty < 2 * DT_H);
+        if (mine) {
+            sP[lj][li] = tp[u];
+            sV[lj][li] = tv[u];
+            sM[lj][li] = tm[u];
         }
     }
     __syncthreads();
@@ -647,8 +652,8 @@ __global__ void __launch_bounds__(DT_X* DT_Y, MIN_BLOCKS) k_detect(View v, const
         const bool changed = (flags & DTF_S5) ? detect_patch<5>(k, sP, sV, sM, li, lj, tb.x, tb.y, tb.z, g, c)
                                               : detect_patch<3>(k, sP, sV, sM, li, lj, tb.x, tb.y, tb.z, g, c);
         if (changed) {
-            v.layer(sp.slot, L_GROUND)[cell] = g;
-            v.layer(sp.slot, L_GROUNDPATCH)[cell] = c;
+            L0[L_GROUND * N2 + cell] = g;
+            L0[L_GROUNDPATCH * N2 + cell] = c;
         }
     }
     if (v.skew.sk) {
@@ -1133,35 +1138,64 @@ __global__ void __launch_bounds__(MAXT, MIN_CTAS) k_spiral_skew(View v, const Sl
 // ------------------------------------------------------------------------------------------
 // phase 4: labelling (:146-196)
 // ------------------------------------------------------------------------------------------
+// LABEL_ILP points per thread (strided by the block, so every access stays coalesced): the streaming loads of all
+// of them are issued first, then the two gathers each, then the arithmetic -- the kernel is bound by memory latency.
+constexpr int LABEL_ILP = 4;
+
 __global__ void __launch_bounds__(256) k_label(View v, const SlotParams* __restrict__ batch) {
     const SlotParams& sp = batch[blockIdx.y];
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= sp.n_points) return;
     const Const& k = v.k;
     const size_t base = (size_t)sp.slot * v.pcap;
-    const uint32_t code = v.code[base + i];
-    const uint32_t cls = code >> 24;
-    const int cell = (int)(code & 0xffffffu);
-    uint8_t label = GG_LABEL_ABSENT;
-    if (cls == PC_OUTLIER) {
-        label = GG_LABEL_GROUND;
-    } else if (cls == PC_KEPT || cls == PC_IGNORED) {
-        const double groundheight = (double)v.layer(sp.slot, L_GROUND)[cell];
-        const float variance = v.layer(sp.slot, L_VARIANCE)[cell];
-        const float dist = v.dist[base + i];
-        const float z = __uint_as_float(v.kz[base + i].y);
-        // std::max(std::min((f * dist) / variance * thres, thres), obs_thres) with C++ min/max semantics
-        const double a = __dmul_rn(__ddiv_rn(__dmul_rn(k.lab_fac, (double)dist), (double)variance), k.lab_thres);
-        double t = (k.lab_thres < a) ? k.lab_thres : a;
-        t = (t < k.lab_obs) ? k.lab_obs : t;
-        if (__dadd_rn(t, groundheight) < (double)z) {
-            label = GG_LABEL_NONGROUND;
-            atomicAdd(v.layer(sp.slot, L_OBSTACLES) + cell, 1.0f);  // small exact integers: order free
-        } else {
-            label = GG_LABEL_GROUND;
-        }
+    const int i0 = blockIdx.x * (256 * LABEL_ILP) + threadIdx.x;
+    const int n = sp.n_points;
+    if (i0 >= n) return;
+    const float* L0 = v.layer(sp.slot, 0);
+    const float* G = L0 + L_GROUND * k.N2;
+    const float* V = L0 + L_VARIANCE * k.N2;
+    float* OBS = v.layer(sp.slot, L_OBSTACLES);
+
+    uint32_t code[LABEL_ILP];
+    float dist[LABEL_ILP], z[LABEL_ILP], gh[LABEL_ILP], var[LABEL_ILP];
+#pragma unroll
+    for (int u = 0; u < LABEL_ILP; ++u) {
+        const int i = i0 + u * 256;
+        const bool in = i < n;
+        code[u] = in ? v.code[base + i] : (PC_ABSENT << 24);
+        dist[u] = in ? v.dist[base + i] : 0.0f;
+        z[u] = in ? __uint_as_float(v.kz[base + i].y) : 0.0f;
     }
-    v.labels[base + i] = label;
+#pragma unroll
+    for (int u = 0; u < LABEL_ILP; ++u) {
+        const uint32_t cls = code[u] >> 24;
+        const int cell = (int)(code[u] & 0xffffffu);
+        const bool use = cls == PC_KEPT || cls == PC_IGNORED;
+        gh[u] = use ? G[cell] : 0.0f;
+        var[u] = use ? V[cell] : 1.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < LABEL_ILP; ++u) {
+        const int i = i0 + u * 256;
+        if (i >= n) break;
+        const uint32_t cls = code[u] >> 24;
+        const int cell = (int)(code[u] & 0xffffffu);
+        uint8_t label = GG_LABEL_ABSENT;
+        if (cls == PC_OUTLIER) {
+            label = GG_LABEL_GROUND;
+        } else if (cls == PC_KEPT || cls == PC_IGNORED) {
+            const double groundheight = (double)gh[u];
+            // std::max(std::min((f * dist) / variance * thres, thres), obs_thres) with C++ min/max semantics
+            const double a = __dmul_rn(__ddiv_rn(__dmul_rn(k.lab_fac, (double)dist[u]), (double)var[u]), k.lab_thres);
+            double t = (k.lab_thres < a) ? k.lab_thres : a;
+            t = (t < k.lab_obs) ? k.lab_obs : t;
+            if (__dadd_rn(t, groundheight) < (double)z[u]) {
+                label = GG_LABEL_NONGROUND;
+                atomicAdd(OBS + cell, 1.0f);  // small exact integers: order free
+            } else {
+                label = GG_LABEL_GROUND;
+            }
+        }
+        v.labels[base + i] = label;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1436,7 +1470,7 @@ int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int 
     ++launches;
     if (stop_after == 3) return launches;
 
-    GG_LAUNCH(K_LABEL, k_label<<<dim3(pblocks, count), 256, 0, st>>>(v, batch));
+    GG_LAUNCH(K_LABEL, k_label<<<dim3(max(1, cdiv(max_points, 256 * LABEL_ILP)), count), 256, 0, st>>>(v, batch));
     ++launches;
     return launches;
 }

@@ -3,11 +3,8 @@ run() { # label, bench-args, env...
   label=$1; shift; bargs=$1; shift
   env "$@" timeout 200 python bench.py --steps 16 --no-cpu-baseline --no-e2e $bargs > gpurun_out/sw_$label.json 2>gpurun_out/sw_$label.err
   python -c "
-import json;d=json.load(open('gpurun_out/sw_$label.json'));r=d['roofline']['kernel_avg_launch_us'];print('$label', 'value', round(d['value']), round(d['ms_per_step'],3), 'spiral', r['k_spiral'], 'detect', r['k_detect'], 'raster', r['k_rasterize'], 'single', round(d['single_stream']['ms_per_scan'],3))" || tail -5 gpurun_out/sw_$label.err
+import json;d=json.load(open('gpurun_out/sw_$label.json'));r=d['roofline']['kernel_avg_launch_us'];print('$label', 'value', round(d['value']), round(d['ms_per_step'],3), 'spiral', r['k_spiral'], 'detect', r['k_detect'], 'raster', r['k_rasterize'], 'label', r['k_label'], 'single', round(d['single_stream']['ms_per_scan'],3))" || tail -5 gpurun_out/sw_$label.err
 }
-run r3_s1 "" GG_STREAMS=1
-run r4_s1 "" GG_STREAMS=1 GG_RASTER_OCC=4
-run r3_s4 "" A=1
-run r4_s4 "" GG_RASTER_OCC=4
-run r4_s4_296 "--streams 296" GG_RASTER_OCC=4
-run r4_s4_m96 "" GG_RASTER_OCC=4 GG_SPIRAL_M=96
+run s1 "" GG_STREAMS=1
+run s4 "" A=1
+run s4b "" A=1
