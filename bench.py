@@ -514,7 +514,10 @@ def main():
     path_bytes = (45.0 * P_mean + 72.0 * N2 + 16.0 * N2) * B     # + roll every step
     path_gbs = path_bytes / (ms_dev / args.steps * 1e-3) / 1e9
     roofline_path = {"bound": "hbm", "algorithmic_bytes_per_step": path_bytes, "achieved": path_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": path_gbs / peak, "formula": "(45 P + 72 N^2 + 16 N^2 roll) x streams / step time"}
+                     "frac": path_gbs / peak, "formula": "(45 P + 72 N^2 + 16 N^2 roll) x streams / step time",
+                     "fused_lower_bound": {"formula": "(17 P + 20 N^2) x streams (points in, labels out, G/C in+out, E in; SURVEY 8d)",
+                                           "bytes_per_step": (17.0 * P_mean + 20.0 * N2) * B,
+                                           "frac": (17.0 * P_mean + 20.0 * N2) * B / (ms_dev / args.steps * 1e-3) / 1e9 / peak}}
 
     # ---- CPU baseline: the oracle replaying stream 0 of rank 0 on this host (bounded sample)
     cpu = None

@@ -140,42 +140,83 @@ __device__ int block_exclusive_scan_1024(const int* in, int* out, int n) {
 // ------------------------------------------------------------------------------------------
 // GroundGrid::update (GroundGrid.cpp:96-133,143): new(r, c) = old(r + shift_i, c + shift_j);
 // exposed cells: ground = -(T * (cx, cy, 0)).z in fp64, groundpatch = 0.
+// Four consecutive cells per thread: the eight (shifted, hence unaligned but contiguous) loads are issued together and,
+// when N*N is a multiple of 4 (every layer then starts 16-byte aligned), the results leave as 16-byte stores.
+constexpr int ROLL_ILP = 4;
+
 __global__ void __launch_bounds__(256) k_roll_gather(View v, const SlotParams* __restrict__ batch) {
     const SlotParams& sp = batch[blockIdx.y];
     if (sp.shift_i == 0 && sp.shift_j == 0) return;
     const Const& k = v.k;
-    const int cell = blockIdx.x * 256 + threadIdx.x;
-    if (cell >= k.N2) return;
+    const int cell0 = (blockIdx.x * 256 + threadIdx.x) * ROLL_ILP;
+    if (cell0 >= k.N2) return;
     const int N = k.N;
-    const int r = cell % N, c = cell / N;
-    const int orr = r + sp.shift_i, occ = c + sp.shift_j;
     const float* G = v.layer(sp.slot, L_GROUND);
     const float* C = v.layer(sp.slot, L_GROUNDPATCH);
     float* sg = v.roll_scratch + (size_t)sp.slot * 2 * k.N2;
     float* sc = sg + k.N2;
-    if (orr >= 0 && orr < N && occ >= 0 && occ < N) {
-        sg[cell] = G[orr + occ * N];
-        sc[cell] = C[orr + occ * N];
+    float g[ROLL_ILP], c[ROLL_ILP];
+    bool seed[ROLL_ILP];
+#pragma unroll
+    for (int u = 0; u < ROLL_ILP; ++u) {
+        const int cell = cell0 + u;
+        const int r = cell % N, cc = cell / N;
+        const int orr = r + sp.shift_i, occ = cc + sp.shift_j;
+        const bool live = cell < k.N2;
+        seed[u] = live && !(orr >= 0 && orr < N && occ >= 0 && occ < N);
+        const bool ld = live && !seed[u];
+        g[u] = ld ? G[orr + occ * N] : 0.0f;
+        c[u] = ld ? C[orr + occ * N] : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < ROLL_ILP; ++u)
+        if (seed[u]) {
+            const int cell = cell0 + u;
+            const int r = cell % N, cc = cell / N;
+            // grid_map getPositionFromIndex: pos + (len/2 - res/2) + res * (-(double)index)
+            const double off = __dsub_rn(k.half, __dmul_rn(0.5, k.res));
+            const double x = __dadd_rn(__dadd_rn(sp.px, off), __dmul_rn(k.res, (double)(-r)));
+            const double y = __dadd_rn(__dadd_rn(sp.py, off), __dmul_rn(k.res, (double)(-cc)));
+            // tf2::Transform * Vector3(x, y, 0): row2.dot(v) + origin.z
+            const double tz = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(sp.t20, x), __dmul_rn(sp.t21, y)), __dmul_rn(sp.t22, 0.0)), sp.t23);
+            g[u] = (float)(-tz);
+            c[u] = 0.0f;
+        }
+    if ((k.N2 & 3) == 0) {
+        *reinterpret_cast<float4*>(sg + cell0) = make_float4(g[0], g[1], g[2], g[3]);
+        *reinterpret_cast<float4*>(sc + cell0) = make_float4(c[0], c[1], c[2], c[3]);
     } else {
-        // grid_map getPositionFromIndex: pos + (len/2 - res/2) + res * (-(double)index)
-        const double off = __dsub_rn(k.half, __dmul_rn(0.5, k.res));
-        const double x = __dadd_rn(__dadd_rn(sp.px, off), __dmul_rn(k.res, (double)(-r)));
-        const double y = __dadd_rn(__dadd_rn(sp.py, off), __dmul_rn(k.res, (double)(-c)));
-        // tf2::Transform * Vector3(x, y, 0): row2.dot(v) + origin.z
-        const double tz = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(sp.t20, x), __dmul_rn(sp.t21, y)), __dmul_rn(sp.t22, 0.0)), sp.t23);
-        sg[cell] = (float)(-tz);
-        sc[cell] = 0.0f;
+#pragma unroll
+        for (int u = 0; u < ROLL_ILP; ++u)
+            if (cell0 + u < k.N2) {
+                sg[cell0 + u] = g[u];
+                sc[cell0 + u] = c[u];
+            }
     }
 }
 
 __global__ void __launch_bounds__(256) k_roll_commit(View v, const SlotParams* __restrict__ batch) {
     const SlotParams& sp = batch[blockIdx.y];
     if (sp.shift_i == 0 && sp.shift_j == 0) return;
-    const int cell = blockIdx.x * 256 + threadIdx.x;
-    if (cell >= v.k.N2) return;
-    const float* sg = v.roll_scratch + (size_t)sp.slot * 2 * v.k.N2;
-    v.layer(sp.slot, L_GROUND)[cell] = sg[cell];
-    v.layer(sp.slot, L_GROUNDPATCH)[cell] = sg[v.k.N2 + cell];
+    const int N2 = v.k.N2;
+    const int cell0 = (blockIdx.x * 256 + threadIdx.x) * ROLL_ILP;
+    if (cell0 >= N2) return;
+    const float* sg = v.roll_scratch + (size_t)sp.slot * 2 * N2;
+    float* G = v.layer(sp.slot, L_GROUND);
+    float* C = v.layer(sp.slot, L_GROUNDPATCH);
+    if ((N2 & 3) == 0) {
+        const float4 a = *reinterpret_cast<const float4*>(sg + cell0);
+        const float4 b = *reinterpret_cast<const float4*>(sg + N2 + cell0);
+        *reinterpret_cast<float4*>(G + cell0) = a;
+        *reinterpret_cast<float4*>(C + cell0) = b;
+    } else {
+#pragma unroll
+        for (int u = 0; u < ROLL_ILP; ++u)
+            if (cell0 + u < N2) {
+                G[cell0 + u] = sg[cell0 + u];
+                C[cell0 + u] = sg[N2 + cell0 + u];
+            }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -531,7 +572,9 @@ __global__ void k_build_detect_table(View v, float4* __restrict__ tab) {
     const float e = v.expected[cell];
     int flags = 0;
     if (!((double)sqdist <= k.psc_sq)) flags |= DTF_S5;
-    if (!(i < 2 || j < 2 || i >= N - 2 || j >= N - 2)) flags |= DTF_INNER;  // union of the four sections, :325-328
+    // union of the four sections, :325-328: first index in [2, 2 * (N / 2) - 2) (the upper half starts at N / 2 and has
+    // N / 2 - 2 entries: one row short of N - 2 when N is odd), second index in [2, N - 2)
+    if (i >= 2 && i < 2 * (N / 2) - 2 && j >= 2 && j < N - 2) flags |= DTF_INNER;
     const int cidx = N / 2 - 1;
     const float fx = __fsub_rn((float)i, (float)cidx), fy = __fsub_rn((float)j, (float)cidx);
     if (__dmul_rn(__dadd_rn(__dmul_rn((double)fx, (double)fx), __dmul_rn((double)fy, (double)fy)), k.res_sq) > 12.0) flags |= DTF_FAR;  // :463
@@ -1388,7 +1431,7 @@ struct Mark {
     } while (0)
 
 int launch_roll(const View& v, const SlotParams* batch, int count, cudaStream_t st, Profiler* prof) {
-    dim3 grid(cdiv(v.k.N2, 256), count);
+    dim3 grid(cdiv(v.k.N2, 256 * ROLL_ILP), count);
     GG_LAUNCH(K_ROLL_GATHER, k_roll_gather<<<grid, 256, 0, st>>>(v, batch));
     GG_LAUNCH(K_ROLL_COMMIT, k_roll_commit<<<grid, 256, 0, st>>>(v, batch));
     return 2;

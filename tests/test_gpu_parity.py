@@ -114,6 +114,29 @@ def test_stream_with_rolling_prior_outliers_and_yaw():
     assert n_out >= 0
 
 
+def test_odd_cell_count_with_rolls():
+    """N = 101 (odd: layers are not 16-byte aligned, the roll kernels take their scalar path; the spiral centre
+    cell sits off the geometric centre)."""
+    dim, res = 33.33, 0.33
+    g, o = make_pair(dim, res)
+    assert g.n == 101
+    scene = synth.make_scene(seed=41)
+    for k in range(4):
+        ex, ey = 0.7 * k, -0.45 * k
+        pts, org = synth.scan_64(scene, ego_xy=(ex, ey), seed=4100 + k)
+        T = synth.base_from_map(ex, ey, 0.0, base_z=0.0, pitch=0.005)
+        if k == 0:
+            g.init_map(ex, ey, 0.0)
+            o.init_map(ex, ey, 0.0)
+        else:
+            assert int(g.update_pose(ex, ey, T)) == o.update(ex, ey, T)
+            assert_layers_equal(g, o, ("ground", "groundpatch"), f"scan {k} after roll")
+        labels = g.filter_cloud(pts, org, 0.0)
+        lab_o, _, _ = o.filter_cloud(pts, org, 0.0, threads=1)
+        assert np.array_equal(labels, lab_o), f"scan {k}: {(labels != lab_o).sum()} labels differ"
+        assert_layers_equal(g, o, ("points",) + LIVE, f"scan {k}")
+
+
 def test_outlier_branch_is_exercised():
     g, o = make_pair(99.0, 0.33)
     scene = synth.make_scene(seed=3)
