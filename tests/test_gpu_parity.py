@@ -137,6 +137,50 @@ def test_odd_cell_count_with_rolls():
         assert_layers_equal(g, o, ("points",) + LIVE, f"scan {k}")
 
 
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_random_geometry_and_config(seed):
+    """Seeded random map geometry (odd and even cell counts, 0.2-0.6 m cells), random configuration within sane
+    ranges, three scans with rolls, yaw and a pitched base frame, some points pushed below ground (outlier branch)."""
+    rng = np.random.default_rng(9000 + seed)
+    res = float(np.float32(rng.choice([0.2, 0.25, 0.33, 0.4, 0.5, 0.6])))
+    n_target = int(rng.integers(41, 260))
+    dim = n_target * res
+    cfg = dict(point_count_cell_variance_threshold=int(rng.integers(2, 20)),
+               max_ring=int(rng.choice([1024, 60, 48])),
+               distance_factor=float(rng.choice([0.0001, 0.0002, 0.0005])),
+               minimum_distance_factor=float(rng.choice([0.0005, 0.001, 0.002])),
+               miminum_point_height_threshold=float(rng.uniform(0.2, 0.5)),
+               minimum_point_height_obstacle_threshold=float(rng.uniform(0.05, 0.2)),
+               outlier_tolerance=float(rng.uniform(0.05, 0.2)),
+               ground_patch_detection_minimum_point_count_threshold=float(rng.uniform(0.1, 0.5)),
+               patch_size_change_distance=float(rng.uniform(5.0, 40.0)),
+               occupied_cells_decrease_factor=float(rng.choice([5.0, 3.0, 10.0, 1.5])),
+               occupied_cells_point_count_factor=float(rng.choice([20.0, 10.0, 40.0])),
+               min_outlier_detection_ground_confidence=float(rng.uniform(0.5, 2.0)))
+    full = bool(seed & 1)
+    g, o = make_pair(dim, res, full=full, **cfg)
+    assert g.n == o.n
+    scene = synth.make_scene(seed=9000 + seed, stream_len=15.0, undulation=0.2)
+    step = float(rng.uniform(0.3, 2.0))
+    for k in range(3):
+        ex, ey, yaw = step * k, -0.6 * step * k, 0.02 * k
+        pts, org = synth.scan_64(scene, ego_xy=(ex, ey), yaw=yaw, seed=9100 + 10 * seed + k)
+        if k:
+            idx = rng.choice(len(pts), 300, replace=False)
+            pts["z"][idx] -= rng.uniform(0.3, 1.0, 300).astype(np.float32)
+        T = synth.base_from_map(ex, ey, yaw, base_z=0.0, pitch=0.008)
+        if k == 0:
+            g.init_map(ex, ey, 0.0)
+            o.init_map(ex, ey, 0.0)
+        else:
+            assert int(g.update_pose(ex, ey, T)) == o.update(ex, ey, T)
+        labels = g.filter_cloud(pts, org, 0.01 * k)
+        lab_o, _, _ = o.filter_cloud(pts, org, 0.01 * k, threads=1)
+        ctx = f"seed {seed} N {g.n} res {res} scan {k}"
+        assert np.array_equal(labels, lab_o), f"{ctx}: {(labels != lab_o).sum()} labels differ"
+        assert_layers_equal(g, o, ("points",) + LIVE + (DEAD if full else ()), ctx)
+
+
 def test_outlier_branch_is_exercised():
     g, o = make_pair(99.0, 0.33)
     scene = synth.make_scene(seed=3)
