@@ -139,32 +139,47 @@ class HostPacker {
     std::atomic<uint64_t> copied{0};
     std::atomic<uint64_t> pack_ns{0}, slot_wait_ns{0};  // summed over the worker threads (diagnostics)
 
-    // jobs must stay alive until every job is either packed or claimed raw; chunks go out in job order;
-    // job j is packed job number seq_base + j
+    // jobs must stay alive until every job is either packed or claimed raw (or cancel() has returned); chunks go
+    // out in job order; job j is packed job number seq_base + j
     void start(std::vector<PackJob>* jobs, uint64_t seq_base) {
         while (busy_.load(std::memory_order_acquire) != 0) std::this_thread::yield();  // stragglers of the previous run
-        seq_base_ = seq_base;
-        chunks_.clear();
-        first_chunk_.clear();
+        std::vector<std::pair<int, int>> chunks;
+        std::vector<size_t> first_chunk;
         for (size_t j = 0; j < jobs->size(); ++j) {
             PackJob& job = (*jobs)[j];
             const int nch = (int)std::max<size_t>(1, (job.n + kChunk - 1) / kChunk);
             job.remaining.store(nch, std::memory_order_relaxed);
-            first_chunk_.push_back(chunks_.size());
-            for (int c = 0; c < nch; ++c) chunks_.push_back({(int)j, c});
+            first_chunk.push_back(chunks.size());
+            for (int c = 0; c < nch; ++c) chunks.push_back({(int)j, c});
         }
         {
+            // everything a claim reads changes under the claim lock, so a worker that wakes up late sees either the
+            // finished previous run (nothing to claim) or this one completely
             std::lock_guard<std::mutex> g(claim_mu_);
+            chunks_.swap(chunks);
+            first_chunk_.swap(first_chunk);
+            jobs_ = jobs;
+            seq_base_ = seq_base;
             next_ = 0;
             limit_ = chunks_.size();
             raw_from_ = (int)jobs->size();
+            cancel_.store(false, std::memory_order_relaxed);
         }
         {
             std::lock_guard<std::mutex> g(mu_);
-            jobs_ = jobs;
             ++epoch_;
         }
         cv_.notify_all();
+    }
+    // Error path of the caller: nothing more is claimed, chunks in flight are waited for; afterwards the job list
+    // may be destroyed.
+    void cancel() {
+        {
+            std::lock_guard<std::mutex> g(claim_mu_);
+            limit_ = next_;
+            cancel_.store(true, std::memory_order_release);
+        }
+        while (inflight_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
     }
     // Take the last job nobody has started packing yet out of the packers' hands (it will be sent as
     // plain 32-byte records).  Returns its index or -1.
@@ -186,30 +201,40 @@ class HostPacker {
 
   private:
     bool work_one(bool may_wait) {
-        std::vector<PackJob>* jobs = jobs_;
-        if (!jobs) return false;
+        std::vector<PackJob>* jobs;
         size_t c;
+        uint64_t seq;
         {
             std::lock_guard<std::mutex> g(claim_mu_);
-            if (next_ >= limit_) return false;
-            if (!may_wait && seq_base_ + (uint64_t)chunks_[next_].first >= copied.load(std::memory_order_acquire) + (uint64_t)slots_) return false;
+            jobs = jobs_;
+            if (!jobs || next_ >= limit_) return false;
+            seq = seq_base_ + (uint64_t)chunks_[next_].first;
+            if (!may_wait && seq >= copied.load(std::memory_order_acquire) + (uint64_t)slots_) return false;
             c = next_++;
+            inflight_.fetch_add(1, std::memory_order_acq_rel);
         }
-        const uint64_t seq = seq_base_ + (uint64_t)chunks_[c].first;
+        const std::pair<int, int> chunk = chunks_[c];  // chunks_ only changes in start(), which waits for busy_ == 0
         const auto t0 = std::chrono::steady_clock::now();
+        bool go = true;
         while (seq >= copied.load(std::memory_order_acquire) + (uint64_t)slots_) {  // the slot's previous cloud is still on its way
-            if (stop_) return false;
+            if (stop_ || cancel_.load(std::memory_order_acquire)) {
+                go = false;
+                break;
+            }
             std::this_thread::sleep_for(std::chrono::microseconds(20));
         }
         const auto t1 = std::chrono::steady_clock::now();
-        PackJob& job = (*jobs)[chunks_[c].first];
-        const size_t i0 = (size_t)chunks_[c].second * kChunk;
-        pack_range(job.src, job.n, slot_of(seq), i0, std::min(job.n, i0 + kChunk), true);
-        job.remaining.fetch_sub(1, std::memory_order_release);
+        if (go) {
+            PackJob& job = (*jobs)[chunk.first];
+            const size_t i0 = (size_t)chunk.second * kChunk;
+            pack_range(job.src, job.n, slot_of(seq), i0, std::min(job.n, i0 + kChunk), true);
+            job.remaining.fetch_sub(1, std::memory_order_release);
+        }
         const auto t2 = std::chrono::steady_clock::now();
         slot_wait_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count(), std::memory_order_relaxed);
         pack_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t2 - t1).count(), std::memory_order_relaxed);
-        return true;
+        inflight_.fetch_sub(1, std::memory_order_acq_rel);
+        return go;
     }
     void loop() {
         uint64_t seen = 0;
@@ -238,7 +263,8 @@ class HostPacker {
     uint64_t seq_base_ = 0;
     size_t next_ = 0, limit_ = 0;
     int raw_from_ = 0;
-    std::atomic<int> busy_{0};
+    std::atomic<int> busy_{0}, inflight_{0};
+    std::atomic<bool> cancel_{false};
     uint64_t epoch_ = 0;
     std::atomic<bool> stop_{false};
 };
@@ -1325,6 +1351,13 @@ int gg_filter_cloud_batch_begin(gg_handle h, int count, const gg_scan_desc* scan
         h->packer->slot_wait_ns = 0;
         uint64_t idle_ns = 0;
         h->packer->start(&jobs, seq_base);
+        struct CancelOnExit {  // an error return below must not leave packers working on `jobs`
+            HostPacker* p;
+            bool armed = true;
+            ~CancelOnExit() {
+                if (armed) p->cancel();
+            }
+        } pack_guard{h->packer};
         int front = 0, back = count, raw_issued = 0, n_copies = 0;
         while (front < back) {
             poll_copies();
@@ -1370,6 +1403,7 @@ int gg_filter_cloud_batch_begin(gg_handle h, int count, const gg_scan_desc* scan
         h->last_pack_us = h->packer->pack_ns.load() / 1000;
         h->last_slot_wait_us = h->packer->slot_wait_ns.load() / 1000;
         h->last_idle_us = idle_ns / 1000;
+        pack_guard.armed = false;  // every job is packed or was sent raw
         for (int g = 0; g < h->n_streams; ++g)
             if ((rc = flush(g))) return rc;
         h->batch_parity ^= 1;
@@ -1464,6 +1498,76 @@ static int pack_whole_cloud(const gg_point* src, size_t n, unsigned char* dst, b
 int gg_host_pack_cloud(const gg_point* src, size_t n, unsigned char* dst) { return pack_whole_cloud(src, n, dst, false); }
 // same with plain (cache-allocating) stores
 int gg_host_pack_cloud_cached(const gg_point* src, size_t n, unsigned char* dst) { return pack_whole_cloud(src, n, dst, true); }
+
+// host-only self-test of the packer pool (no CUDA): `rounds` batches of n_jobs clouds go through a ring of
+// `ring_slots` staging slots; this thread plays the feeder of gg_filter_cloud_batch_begin -- it checks every packed
+// cloud against the single-threaded packing, "completes" its copy `lag` jobs later (so packers have to wait for
+// slots), takes some jobs away from the back like the raw path does, and cancels the last batch half way.
+// Returns 0, or a negative code telling which check failed.
+int gg_host_packer_selftest(int threads, int n_jobs, size_t n_points, int ring_slots, int rounds, int lag) {
+    if (threads < 1 || n_jobs < 1 || ring_slots < 2 || rounds < 1 || lag < 0 || lag >= ring_slots) return GG_E_ARG;
+    const size_t n_pad = (n_points + 7) & ~(size_t)7, stride = 14 * n_pad + 64;
+    std::vector<std::vector<gg_point>> src(n_jobs);
+    std::vector<std::vector<unsigned char>> want(n_jobs);
+    uint32_t lcg = 12345u;
+    for (int j = 0; j < n_jobs; ++j) {
+        const size_t n = n_points - (size_t)(j % 5);  // ragged sizes
+        src[j].resize(n);
+        unsigned char* raw = reinterpret_cast<unsigned char*>(src[j].data());
+        for (size_t b = 0; b < n * sizeof(gg_point); ++b) {
+            lcg = lcg * 1664525u + 1013904223u;
+            raw[b] = (unsigned char)(lcg >> 24);
+        }
+        want[j].assign(stride + 32, 0);
+        unsigned char* w = want[j].data() + ((32 - (reinterpret_cast<uintptr_t>(want[j].data()) & 31)) & 31);
+        pack_whole_cloud(src[j].data(), n, w, false);
+    }
+    auto want_ptr = [&](int j) { return want[j].data() + ((32 - (reinterpret_cast<uintptr_t>(want[j].data()) & 31)) & 31); };
+    std::vector<unsigned char> ring_mem((size_t)ring_slots * stride + 64);
+    unsigned char* ring = ring_mem.data() + ((64 - (reinterpret_cast<uintptr_t>(ring_mem.data()) & 63)) & 63);
+    HostPacker packer(threads);
+    packer.set_ring(ring, stride, ring_slots);
+    uint64_t issued = 0;
+    for (int round = 0; round < rounds; ++round) {
+        std::vector<PackJob> jobs(n_jobs);
+        for (int j = 0; j < n_jobs; ++j) {
+            jobs[j].src = src[j].data();
+            jobs[j].n = src[j].size();
+        }
+        const bool cancel_round = round == rounds - 1;
+        const uint64_t base = issued;
+        packer.start(&jobs, base);
+        int front = 0, back = n_jobs, spins = 0;
+        while (front < back) {
+            if (issued >= (uint64_t)lag) packer.copied.store(issued - (uint64_t)lag, std::memory_order_release);
+            if (cancel_round && front >= n_jobs / 2) {
+                packer.cancel();
+                break;
+            }
+            if (packer.packed(jobs[front])) {
+                const size_t np = (jobs[front].n + 7) & ~(size_t)7;
+                if (std::memcmp(packer.slot_of(base + front), want_ptr(front), 14 * np) != 0) return -100 - front;
+                ++issued;
+                ++front;
+                spins = 0;
+                continue;
+            }
+            if ((front + round) % 3 == 0) {
+                const int j = packer.claim_raw_from_back();
+                if (j >= 0) {
+                    if (j != back - 1) return -50;
+                    back = j;
+                    continue;
+                }
+            }
+            if (!packer.help()) std::this_thread::yield();
+            if (++spins > 200000000) return -60;  // stuck
+        }
+        packer.copied.store(issued, std::memory_order_release);  // all copies of this batch "done"
+    }
+    return GG_OK;
+}
+
 
 // number of host threads that repack clouds in gg_filter_cloud_batch (0: packing disabled or not used yet)
 int gg_host_pack_threads(gg_handle h) { return (h && h->host_pack && h->packer) ? h->packer->threads() + 1 : 0; }

@@ -46,5 +46,6 @@ int gg_host_spiral_records(int n, float resolution, int dist, uint32_t* recs, in
 int gg_host_move_map(double res, double* pos_xy, double nx, double ny, int* shift_ij);
 int gg_host_pack_cloud(const gg_point* src, size_t n, unsigned char* dst);
 int gg_host_pack_cloud_cached(const gg_point* src, size_t n, unsigned char* dst);
+int gg_host_packer_selftest(int threads, int n_jobs, size_t n_points, int ring_slots, int rounds, int lag);
 int gg_host_spiral_skew(int n, int* header, int* pattern, int* lane_begin, int* lane_end, int* cell_home, int* irr_level_start, uint32_t* irr_recs, int irr_cap_words);
 }

@@ -394,3 +394,19 @@ def test_skewed_spiral_tables_emulation(dim, res):
     Gf[m], Cf[m] = SKg[home[m, 0]], SKc[home[m, 0]]
     assert np.array_equal(o.layer("ground"), Gf.reshape(n, n, order="F"))
     assert np.array_equal(o.layer("groundpatch"), Cf.reshape(n, n, order="F"))
+
+
+@pytest.mark.parametrize("threads,n_jobs,n_points,ring,rounds,lag", [(4, 40, 20000, 8, 4, 3), (3, 17, 50001, 4, 3, 1),
+                                                                     (6, 64, 3000, 5, 6, 4), (2, 9, 100, 2, 3, 0),
+                                                                     (8, 96, 16385, 32, 5, 6)])
+def test_packer_pool_ring_claims_and_cancel(threads, n_jobs, n_points, ring, rounds, lag):
+    """The worker pool of gg_filter_cloud_batch without CUDA: ragged clouds through a small staging ring whose slots
+    are released `lag` jobs late, jobs taken away from the back (raw path), a cancelled batch, several rounds."""
+    import ctypes as C
+
+    L = capi.load()
+    f = L.gg_host_packer_selftest
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int]
+    for _ in range(3):
+        assert f(threads, n_jobs, n_points, ring, rounds, lag) == 0

@@ -6,5 +6,4 @@ run() { # label, bench-args, env...
 import json;d=json.load(open('gpurun_out/sw_$label.json'));r=d['roofline']['kernel_avg_launch_us'];print('$label', 'value', round(d['value']), round(d['ms_per_step'],3), 'spiral', r['k_spiral'], 'detect', r['k_detect'], 'raster', r['k_rasterize'], 'label', r['k_label'], 'single', round(d['single_stream']['ms_per_scan'],3))" || tail -5 gpurun_out/sw_$label.err
 }
 run s1 "" GG_STREAMS=1
-run s4 "" A=1
-run s4b "" A=1
+run s4 "" GG_STREAMS=4
