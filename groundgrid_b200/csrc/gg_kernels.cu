@@ -317,7 +317,8 @@ __device__ __forceinline__ uint32_t rasterize_point(const View& v, const SlotPar
 // One block = one sort tile (SORT_TILE consecutive points, SORT_THREADS threads): besides the
 // per-point products it leaves the tile's histogram of the LOW key digit (pass 1 of the radix sort
 // needs no separate counting pass) and clears its column of the high-digit table.
-__global__ void __launch_bounds__(SORT_THREADS) k_rasterize(View v, const SlotParams* __restrict__ batch, int nb) {
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) k_rasterize(View v, const SlotParams* __restrict__ batch, int nb) {
     extern __shared__ int s_hist[];
     const SlotParams& sp = batch[blockIdx.y];
     const int D = 1 << v.bits_lo, D2 = 1 << v.bits_hi;
@@ -367,8 +368,8 @@ __global__ void __launch_bounds__(1024) k_sort_scan_hi(View v, const SlotParams*
 // [warps][digits] table, and a thread's rank is the running digit count of earlier rounds + the
 // counts of earlier warps + its rank inside the warp -- two barriers per round, equal digits keep
 // their input order.
-template <bool LAST>
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(View v, const SlotParams* __restrict__ batch, const uint2* __restrict__ kz_in,
+template <bool LAST, int MIN_BLOCKS>
+__global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) k_sort_scatter(View v, const SlotParams* __restrict__ batch, const uint2* __restrict__ kz_in,
                                                                uint2* __restrict__ kz_out, float* __restrict__ vals_out, int shift, int bits, int nb) {
     extern __shared__ int s_run[];  // [D] running per-digit count, then [WARPS][D] u16 counts of the current round
     constexpr int ROUNDS = SORT_TILE / SORT_THREADS;
@@ -589,9 +590,12 @@ __global__ void k_build_detect_table(View v, float4* __restrict__ tab) {
 }
 
 // returns true when (g, c) changed
+// sPV / sPM hold the products count * variance and count * minHeight of every tile entry (the very fmul the
+// reference's cwiseProduct performs, done once per entry instead of once per window position)
 template <int S>
-__device__ __forceinline__ bool detect_patch(const Const& k, const float (*sP)[DT_W], const float (*sV)[DT_W], const float (*sM)[DT_W],
-                                             int li, int lj, float need, float vt, float e, float& g, float& c) {
+__device__ __forceinline__ bool detect_patch(const Const& k, const float (*sP)[DT_W], const float (*sPV)[DT_W], const float (*sPM)[DT_W],
+                                             const float (*sM)[DT_W], int li, int lj, float variance, float need, float vt, float e, float& g,
+                                             float& c) {
     constexpr int H = S / 2;
     const int r0 = li - H, c0 = lj - H;  // block origin in the shared tile (row index = i, col = j)
     const float psum = TreeSum<0, S * S>::run([&](int q) { return sP[c0 + q / S][r0 + q % S]; });
@@ -600,7 +604,6 @@ __device__ __forceinline__ bool detect_patch(const Const& k, const float (*sP)[D
     // early skipping of (almost) empty areas, :364 (both sides integer valued: the float compare is the double one)
     if (psum < need) return false;
 
-    const float variance = sV[lj][li];
     float localmin = sM[c0][r0];
 #pragma unroll
     for (int q = 1; q < S * S; ++q) {
@@ -609,9 +612,8 @@ __device__ __forceinline__ bool detect_patch(const Const& k, const float (*sP)[D
     }
     const float maxVar = (sP[lj][li] >= k.pc_var_thresh_f)
                              ? variance
-                             : __fdiv_rn(TreeSum<0, S * S>::run([&](int q) { return __fmul_rn(sP[c0 + q / S][r0 + q % S], sV[c0 + q / S][r0 + q % S]); }), psum);
-    const float groundlevel =
-        __fdiv_rn(TreeSum<0, S * S>::run([&](int q) { return __fmul_rn(sP[c0 + q / S][r0 + q % S], sM[c0 + q / S][r0 + q % S]); }), psum);
+                             : __fdiv_rn(TreeSum<0, S * S>::run([&](int q) { return sPV[c0 + q / S][r0 + q % S]; }), psum);
+    const float groundlevel = __fdiv_rn(TreeSum<0, S * S>::run([&](int q) { return sPM[c0 + q / S][r0 + q % S]; }), psum);
     const float gd = __fmul_rn(__fsub_rn(groundlevel, og), __fmul_rn(2.0f, oc));
     const float groundDiff = (gd < 1.0f) ? 1.0f : gd;  // std::max(gd, 1.0f)
 
@@ -640,7 +642,7 @@ __device__ __forceinline__ bool detect_patch(const Const& k, const float (*sP)[D
 
 template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(DT_X* DT_Y, MIN_BLOCKS) k_detect(View v, const SlotParams* __restrict__ batch) {
-    __shared__ float sP[DT_R][DT_W], sV[DT_R][DT_W], sM[DT_R][DT_W];
+    __shared__ float sP[DT_R][DT_W], sPV[DT_R][DT_W], sPM[DT_R][DT_W], sM[DT_R][DT_W];
     const SlotParams& sp = batch[blockIdx.z];
     const Const& k = v.k;
     const int N = k.N;
@@ -651,39 +653,42 @@ __global__ void __launch_bounds__(DT_X* DT_Y, MIN_BLOCKS) k_detect(View v, const
     const float* P = L0 + L_COUNT * N2;
     const float* V = L0 + L_VARIANCE * N2;
     const float* M = L0 + L_MINH * N2;
-    // tile + halo (36 x 12): a thread fetches column li = tx of rows ty and ty + 8 (ty < 4) and, for tx < 4, the four
-    // extra halo columns 32 + tx of the same rows -- fixed positions, no div/mod; all global loads are issued before
-    // the first shared store
+    // tile + halo (36 x 12): a thread fetches column tx of rows ty and ty + 8 (ty < 4) and, for tx < 4, the halo
+    // columns 32 + tx of the same rows; four fixed positions o, o + 32, o + 8 N, o + 8 N + 32, every global load issued
+    // before the first shared store.  Outside the map: count 0, variance 0, min FLT_MAX (products 0), as before.
     const int tx = threadIdx.x, ty = threadIdx.y;
+    const int gi = i0 - DT_H + tx, gj = j0 - DT_H + ty;
+    const bool col0 = gi >= 0 && gi < N, col1 = tx < 2 * DT_H && gi + DT_X < N;
+    const bool row0 = gj >= 0 && gj < N, row1 = ty < 2 * DT_H && gj + DT_Y < N;
+    const int o = gi + gj * N;
+    const bool in[4] = {col0 && row0, col1 && row0, col0 && row1, col1 && row1};
+    const int off[4] = {o, o + DT_X, o + DT_Y * N, o + DT_Y * N + DT_X};
     float tp[4], tv[4], tm[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-        const int li = (u & 1) ? DT_X + tx : tx, lj = (u & 2) ? ty + DT_Y : ty;
-        const bool mine = ((u & 1) == 0 || tx < 2 * DT_H) && ((u & 2) == 0 || ty < 2 * DT_H);
-        const int gi = i0 - DT_H + li, gj = j0 - DT_H + lj;
-        const bool in = mine && gi >= 0 && gi < N && gj >= 0 && gj < N;
-        const int g = gi + gj * N;
-        tp[u] = in ? P[g] : 0.0f;
-        tv[u] = in ? V[g] : 0.0f;
-        tm[u] = in ? M[g] : FLT_MAX;
+        tp[u] = in[u] ? P[off[u]] : 0.0f;
+        tv[u] = in[u] ? V[off[u]] : 0.0f;
+        tm[u] = in[u] ? M[off[u]] : FLT_MAX;
     }
     const int i = i0 + tx, j = j0 + ty;
     const bool live = i < N && j < N;
     const int cell = i + j * N;
-    float g = 0.0f, c = 0.0f;
+    float g = 0.0f, c = 0.0f, variance = 0.0f;
     float4 tb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (live) {
         g = L0[L_GROUND * N2 + cell];
         c = L0[L_GROUNDPATCH * N2 + cell];
+        variance = V[cell];
         tb = __ldg(v.detect_tab + cell);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-        const int li = (u & 1) ? DT_X + tx : tx, lj = (u & 2) ? ty + DT_Y : ty;
         const bool mine = ((u & 1) == 0 || tx < 2 * DT_H) && ((u & 2) == 0 || ty < 2 * DT_H);
         if (mine) {
+            const int li = (u & 1) ? DT_X + tx : tx, lj = (u & 2) ? ty + DT_Y : ty;
             sP[lj][li] = tp[u];
-            sV[lj][li] = tv[u];
+            sPV[lj][li] = __fmul_rn(tp[u], tv[u]);
+            sPM[lj][li] = __fmul_rn(tp[u], tm[u]);
             sM[lj][li] = tm[u];
         }
     }
@@ -692,8 +697,8 @@ __global__ void __launch_bounds__(DT_X* DT_Y, MIN_BLOCKS) k_detect(View v, const
     const int flags = __float_as_int(tb.w);
     if (flags & DTF_INNER) {
         const int li = threadIdx.x + DT_H, lj = threadIdx.y + DT_H;
-        const bool changed = (flags & DTF_S5) ? detect_patch<5>(k, sP, sV, sM, li, lj, tb.x, tb.y, tb.z, g, c)
-                                              : detect_patch<3>(k, sP, sV, sM, li, lj, tb.x, tb.y, tb.z, g, c);
+        const bool changed = (flags & DTF_S5) ? detect_patch<5>(k, sP, sPV, sPM, sM, li, lj, variance, tb.x, tb.y, tb.z, g, c)
+                                              : detect_patch<3>(k, sP, sPV, sPM, sM, li, lj, variance, tb.x, tb.y, tb.z, g, c);
         if (changed) {
             L0[L_GROUND * N2 + cell] = g;
             L0[L_GROUNDPATCH * N2 + cell] = c;
@@ -1445,15 +1450,28 @@ int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int 
 
     // radix sort, pass 1 (low digit): the tile histograms come out of k_rasterize itself
     size_t sh = sizeof(int) << v.bits_lo;
-    GG_LAUNCH(K_RASTERIZE, k_rasterize<<<dim3(nb, count), SORT_THREADS, sh, st>>>(v, batch, nb));
+    static const int raster_occ = getenv("GG_RASTER_OCC") ? atoi(getenv("GG_RASTER_OCC")) : 5;
+    if (raster_occ >= 5)
+        GG_LAUNCH(K_RASTERIZE, k_rasterize<5><<<dim3(nb, count), SORT_THREADS, sh, st>>>(v, batch, nb));
+    else
+        GG_LAUNCH(K_RASTERIZE, k_rasterize<4><<<dim3(nb, count), SORT_THREADS, sh, st>>>(v, batch, nb));
     GG_LAUNCH(K_SCAN_LO_CELLS, k_scan_lo_cells<<<2 * count, 1024, 0, st>>>(v, batch, count, nb));
-    GG_LAUNCH(K_SORT_SCATTER1, k_sort_scatter<false><<<dim3(nb, count), SORT_THREADS, sh + ((size_t)(SORT_THREADS / 32) * 2 << v.bits_lo), st>>>(
-                                   v, batch, v.kz, v.kz2, nullptr, 0, v.bits_lo, nb));
+    static const int scatter_occ = getenv("GG_SCATTER_OCC") ? atoi(getenv("GG_SCATTER_OCC")) : 5;
+    if (scatter_occ >= 5)
+        GG_LAUNCH(K_SORT_SCATTER1, (k_sort_scatter<false, 5><<<dim3(nb, count), SORT_THREADS, sh + ((size_t)(SORT_THREADS / 32) * 2 << v.bits_lo), st>>>(
+                                       v, batch, v.kz, v.kz2, nullptr, 0, v.bits_lo, nb)));
+    else
+        GG_LAUNCH(K_SORT_SCATTER1, (k_sort_scatter<false, 4><<<dim3(nb, count), SORT_THREADS, sh + ((size_t)(SORT_THREADS / 32) * 2 << v.bits_lo), st>>>(
+                                       v, batch, v.kz, v.kz2, nullptr, 0, v.bits_lo, nb)));
     // pass 2 (high digit): its histogram was accumulated by the pass-1 scatter; (key2, z2) -> zsorted
     sh = sizeof(int) << v.bits_hi;
     GG_LAUNCH(K_SORT_SCAN2, k_sort_scan_hi<<<count, 1024, 0, st>>>(v, batch, nb));
-    GG_LAUNCH(K_SORT_SCATTER2, k_sort_scatter<true><<<dim3(nb, count), SORT_THREADS, sh + ((size_t)(SORT_THREADS / 32) * 2 << v.bits_hi), st>>>(
-                                   v, batch, v.kz2, nullptr, v.zsorted, v.bits_lo, v.bits_hi, nb));
+    if (scatter_occ >= 5)
+        GG_LAUNCH(K_SORT_SCATTER2, (k_sort_scatter<true, 5><<<dim3(nb, count), SORT_THREADS, sh + ((size_t)(SORT_THREADS / 32) * 2 << v.bits_hi), st>>>(
+                                       v, batch, v.kz2, nullptr, v.zsorted, v.bits_lo, v.bits_hi, nb)));
+    else
+        GG_LAUNCH(K_SORT_SCATTER2, (k_sort_scatter<true, 4><<<dim3(nb, count), SORT_THREADS, sh + ((size_t)(SORT_THREADS / 32) * 2 << v.bits_hi), st>>>(
+                                       v, batch, v.kz2, nullptr, v.zsorted, v.bits_lo, v.bits_hi, nb)));
     launches += 5;
 
     if (v.k.full_layers)
@@ -1463,11 +1481,11 @@ int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int 
     ++launches;
     if (stop_after == 1) return launches;
 
-    static const int detect_occ = getenv("GG_DETECT_OCC") ? atoi(getenv("GG_DETECT_OCC")) : 4;
-    if (detect_occ >= 4)
-        GG_LAUNCH(K_DETECT, k_detect<4><<<dim3(cdiv(v.k.N, DT_X), cdiv(v.k.N, DT_Y), count), dim3(DT_X, DT_Y), 0, st>>>(v, batch));
+    static const int detect_occ = getenv("GG_DETECT_OCC") ? atoi(getenv("GG_DETECT_OCC")) : 5;
+    if (detect_occ >= 5)
+        GG_LAUNCH(K_DETECT, k_detect<5><<<dim3(cdiv(v.k.N, DT_X), cdiv(v.k.N, DT_Y), count), dim3(DT_X, DT_Y), 0, st>>>(v, batch));
     else
-        GG_LAUNCH(K_DETECT, k_detect<3><<<dim3(cdiv(v.k.N, DT_X), cdiv(v.k.N, DT_Y), count), dim3(DT_X, DT_Y), 0, st>>>(v, batch));
+        GG_LAUNCH(K_DETECT, k_detect<4><<<dim3(cdiv(v.k.N, DT_X), cdiv(v.k.N, DT_Y), count), dim3(DT_X, DT_Y), 0, st>>>(v, batch));
     ++launches;
     if (stop_after == 2) return launches;
 
