@@ -463,12 +463,27 @@ __global__ void __launch_bounds__(128) k_cell_stats(View v, const SlotParams* __
     const int wid = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int tiles_i = (k.N + 7) >> 3;
     const int ci = (wid % tiles_i) * 8 + (lane & 7), cj = (wid / tiles_i) * 4 + (lane >> 3);
-    if (ci >= k.N || cj >= k.N) return;
-    const int cell = ci + cj * k.N;
+    const bool live = ci < k.N && cj < k.N;
+    const int cell = live ? ci + cj * k.N : 0;
     const size_t coff = (size_t)sp.slot * k.N2;
-    const int cnt = v.cnt_i[coff + cell];
-    const float* zs = v.zsorted + (size_t)sp.slot * v.pcap + v.cellstart[coff + cell];
+    const int cnt = live ? v.cnt_i[coff + cell] : 0;
+    const float* zs = v.zsorted + (size_t)sp.slot * v.pcap + (live ? v.cellstart[coff + cell] : 0);
     const float oz = sp.oz;
+    // The eight cells of a patch row own one contiguous run of the sorted heights.  Before the (lane-strided, hence
+    // poorly coalesced) per-cell walks start, the warp touches the first lines of its four runs together, one line
+    // per lane, so that those misses overlap instead of being paid one 8-value batch at a time.
+    {
+        const unsigned long long begin = __shfl_sync(0xffffffffu, (unsigned long long)zs, lane & 24);  // column 0 of the row
+        unsigned long long end = live ? (unsigned long long)(zs + cnt) : 0ull;                             // max over the row
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, end, d);
+            end = o > end ? o : end;
+        }
+        const unsigned long long line = begin + (unsigned long long)(lane & 7) * 128;  // up to 8 lines (1 KB) of each run
+        if (line < end) asm volatile("prefetch.global.L1 [%0];" ::"l"(line));
+    }
+    if (!live) return;
 
     float n = 0.0f, mean = 0.0f, m2 = 0.0f;
     float mn = FLT_MAX;
@@ -476,6 +491,7 @@ __global__ void __launch_bounds__(128) k_cell_stats(View v, const SlotParams* __
     // The recurrence is sequential, the loads are not: fetch up to 8 values at once so that a
     // heavy cell pays one memory latency per 8 points instead of one per point.
     for (int j0 = 0; j0 < cnt; j0 += 8) {
+        if (j0 + 64 < cnt) asm volatile("prefetch.global.L1 [%0];" ::"l"(zs + j0 + 64));  // long cells: stay two lines ahead
         float zb[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) zb[q] = (j0 + q < cnt) ? zs[j0 + q] : 0.0f;
