@@ -456,6 +456,44 @@ def test_overlapped_batches_begin_wait(monkeypatch, unit):
     g.close()
 
 
+def test_batch_on_a_shuffled_subset_of_slots_with_empty_clouds():
+    """Batches need not cover every slot, nor list them in order; a scan may be empty and a label pointer null."""
+    import torch
+
+    dim, res, B = 66.0, 0.33, 7
+    g = capi.GroundGridB200(dim, res, n_slots=B, max_points=131072, full_layers=False)
+    oracles = []
+    for b in range(B):
+        g.init_map(0.2 * b, 0.0, 0.0, slot=b)
+        o = Oracle(dim, res)
+        o.init_map(0.2 * b, 0.0, 0.0)
+        oracles.append(o)
+    empty = np.zeros(0, synth.POINT_DTYPE)
+    for rnd, (slots, empties, no_labels) in enumerate([([5, 2, 0, 6], {2}, {0}), ([1, 6, 3, 5, 4], set(), {4}), ([2, 0], {0}, set())]):
+        clouds, host, labs = {}, {}, {}
+        for b in slots:
+            if b in empties:
+                clouds[b] = (empty, np.array([0.2 * b, 0.0, 1.73], np.float32))
+            else:
+                clouds[b] = synth.scan_64(synth.make_scene(seed=800 + b), ego_xy=(0.2 * b, 0.0), seed=800 + 10 * rnd + b)
+            p = clouds[b][0]
+            host[b] = torch.from_numpy(np.ascontiguousarray(p).view(np.uint8).copy()).pin_memory() if len(p) else None
+            labs[b] = torch.full((max(1, len(p)),), 7, dtype=torch.uint8).pin_memory()
+        descs = g.make_descs(slots, [len(clouds[b][0]) for b in slots], [clouds[b][1] for b in slots], [0.0] * len(slots))
+        g.filter_cloud_batch_ptrs(descs, [host[b].data_ptr() if host[b] is not None else None for b in slots],
+                                  [None if b in no_labels else labs[b].data_ptr() for b in slots])
+        for b in slots:
+            want, _, _ = oracles[b].filter_cloud(clouds[b][0], clouds[b][1], 0.0, threads=1)
+            if b in no_labels:
+                assert (labs[b].numpy() == 7).all()
+            else:
+                assert np.array_equal(labs[b].numpy()[:len(want)], want), f"round {rnd} slot {b}"
+            for name in ("ground", "groundpatch", "points"):
+                r = diff_report(name, g.layer(name, slot=b), oracles[b].layer(name))
+                assert r is None, f"round {rnd} slot {b}: {r}"
+    g.close()
+
+
 def test_batch_path_with_and_without_host_packing(monkeypatch):
     import torch
 
