@@ -340,3 +340,25 @@ def test_next_row_restatements_by_hand():
     # f4: tallies per ground-truth id; absent points do not count
     c = nextrows.eval_counts(np.array([49, 99, 49, 0, 99], np.uint8), np.array([40, 40, 10, 10, 10], np.uint16))
     assert tuple(c[40]) == (1, 1) and tuple(c[10]) == (1, 1) and c.sum() == 4
+
+
+def test_golden_fixtures():
+    """The committed vectors of tests/golden/ (produced by the pure-Python restatement tests/pyref.py): labels, output
+    order and layers of the C++ oracle must match them bit for bit."""
+    import golden_util
+
+    files = golden_util.case_files()
+    assert len(files) >= 3
+    for path in files:
+        case = golden_util.load_case(path)
+        o = Oracle(case["dimension"], case["resolution"])
+        if case["config"]:
+            o.set_config(**golden_util.int_config(case["config"]))
+        o.init_map(0.0, 0.0, 0.0)
+        assert np.array_equal(o.layer("ground"), case["ground_0"]) and np.array_equal(o.layer("groundpatch"), case["groundpatch_0"])
+        for k, s in enumerate(case["scans"]):
+            labels, order, _ = o.filter_cloud(s["points"], s["origin"], s["base_z"], threads=1)
+            assert np.array_equal(labels, s["labels"]), (path, k)
+            assert np.array_equal(order, s["order"]), (path, k)
+        for name, want in case["final"].items():
+            assert np.array_equal(o.layer(name), want, equal_nan=True), (path, name)
