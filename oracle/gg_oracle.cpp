@@ -10,8 +10,10 @@
 // PARITY UNPINNED: the reference repository has no tests, golden vectors or fixtures
 //  and cannot be built here (no Eigen / grid_map / PCL / ROS in the
 // image, no network), so this oracle is pinned only by (1) hand-checkable
-// known-answer cases in tests/test_oracle_known_answers.py and (2) a line-by-line
-// reading of the reference sources cited on every function below.  It DEFINES parity as
+// known-answer cases in tests/test_oracle_known_answers.py, (2) the committed vectors of
+// tests/golden/, which come from the independent pure-Python restatement tests/pyref.py
+// (NOT from the reference), and (3) a line-by-line reading of the reference sources
+// cited on every function below.  It DEFINES parity as
 // the reference's thread_count = 1 execution (the shipped thread_count = 8 has data
 // races, GroundSegmentation.cpp:99-109 vs :234,282-309), with Eigen-3.3.7 reduction
 // order (eigen_redux.hpp) and grid_map_core 1.6.x geometry (gridmap_semantics.hpp).
