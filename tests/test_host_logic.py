@@ -286,7 +286,8 @@ def host_spiral_skew(n):
                 home=home.reshape(n * n, 4), irr_level_start=ils, irr=recs.reshape(-1, 16))
 
 
-@pytest.mark.parametrize("dim,res", [(13.2, 0.33), (33.0, 0.33), (99.0, 0.33), (120.0, 0.33), (120.0, 0.2)])
+@pytest.mark.parametrize("dim,res", [(13.2, 0.33), (33.0, 0.33), (99.0, 0.33), (120.0, 0.33), (120.0, 0.2),
+                                     (33.33, 0.33), (30.5, 0.5), (81.2, 0.4)])   # the last three: odd cell counts (101, 61, 203)
 def test_skewed_spiral_tables_emulation(dim, res):
     """CPU emulation of k_skew -> k_spiral_skew -> k_unskew: lane threads follow the fixed offset
     pattern in (level, ring) space, the irregular warp follows explicit records, neighbourhoods are
