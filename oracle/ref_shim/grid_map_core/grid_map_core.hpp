@@ -1,0 +1,2 @@
+#pragma once
+#include <grid_map_core/GridMap.hpp>

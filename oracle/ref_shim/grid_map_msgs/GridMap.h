@@ -1,0 +1,2 @@
+// TEST INFRASTRUCTURE ONLY (oracle/_ref build): included by the reference headers, unused by the two compiled sources.
+#pragma once

@@ -1,0 +1,10 @@
+// TEST INFRASTRUCTURE ONLY (oracle/_ref build).
+#pragma once
+#include <ros/ros.h>
+namespace std_msgs {
+struct Header {
+    uint32_t seq = 0;
+    ros::Time stamp;
+    std::string frame_id;
+};
+}  // namespace std_msgs

@@ -182,25 +182,19 @@ def test_random_geometry_and_config(seed):
 
 
 def test_golden_fixtures_on_gpu():
-    """The committed vectors of tests/golden/ (tests/golden/make_golden.py) through the C-ABI: labels, output order
-    and layers bit for bit."""
+    """The committed vectors of tests/golden/ -- produced by the reference itself (oracle/_ref, tests/golden/
+    make_golden.py) -- through the C-ABI: creation, map rolls + seeding, labels, output order and all eleven layers bit
+    for bit."""
     import golden_util
 
     files = golden_util.case_files()
-    assert len(files) >= 3
+    assert len(files) >= 5
     for path in files:
         case = golden_util.load_case(path)
         g = capi.GroundGridB200(case["dimension"], case["resolution"], n_slots=1, max_points=16384, full_layers=True)
-        if case["config"]:
-            g.set_config(**golden_util.int_config(case["config"]))
-        g.init_map(0.0, 0.0, 0.0)
-        assert np.array_equal(g.layer("ground"), case["ground_0"]) and np.array_equal(g.layer("groundpatch"), case["groundpatch_0"])
-        for k, s in enumerate(case["scans"]):
-            labels, order, _ = g.filter_cloud(s["points"], s["origin"], s["base_z"], want_index=True)
-            assert np.array_equal(labels, s["labels"]), (path, k)
-            assert np.array_equal(order, s["order"]), (path, k)
-        for name, want in case["final"].items():
-            assert np.array_equal(g.layer(name), want, equal_nan=True), (path, name)
+        assert np.array_equal(g.layer("expectedPoints"), case["expected"])
+        golden_util.replay(case, g, lambda g, x, y, T: g.update_pose(x, y, T),
+                           lambda g, pts, org, bz: g.filter_cloud(pts, org, bz, want_index=True)[:2])
         g.close()
 
 
