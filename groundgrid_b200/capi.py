@@ -97,6 +97,12 @@ def load(build_if_missing=True):
         "gg_run_scans_device": (i, [vp, i, vp, vp, i]),
         "gg_upload_cloud_msg": (i, [vp, i, vp, sz, i, vp, vp]),
         "gg_terrain_image": (i, [vp, i, vp]),
+        "gg_layer_image_u8": (i, [vp, i, C.c_char_p, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+        "gg_get_point_classes": (i, [vp, i, vp, sz]),
+        "gg_detect_ground_patches": (i, [vp, i]),
+        "gg_detect_ground_patch": (i, [vp, i, i, i, i]),
+        "gg_spiral_ground_interpolation": (i, [vp, i, d]),
+        "gg_interpolate_cell": (i, [vp, i, i, i]),
         "gg_eval_accumulate": (i, [vp, i]),
         "gg_eval_read": (i, [vp, vp, i]),
         "gg_profile_enable": (i, [vp, i]),
@@ -335,6 +341,31 @@ class GroundGridB200:
         img = np.zeros((self.n, self.n, 3), np.float32)
         _check(self._l.gg_terrain_image(self._h, slot, _ptr(img)))
         return img
+
+    def layer_image_u8(self, name, slot=0):
+        """(N x N uint8 image indexed [i, j], lower, upper): what toImage<unsigned char, 1> hands to cv::applyColorMap."""
+        img = np.zeros((self.n, self.n), np.uint8)
+        lo, hi = C.c_float(0), C.c_float(0)
+        _check(self._l.gg_layer_image_u8(self._h, slot, name.encode(), _ptr(img), C.byref(lo), C.byref(hi)))
+        return img, lo.value, hi.value
+
+    # -- the reference's per-phase methods
+    def point_classes(self, n, slot=0):
+        codes = np.zeros(n, np.uint32)
+        _check(self._l.gg_get_point_classes(self._h, slot, _ptr(codes), n))
+        return codes
+
+    def detect_ground_patches(self, slot=0):
+        _check(self._l.gg_detect_ground_patches(self._h, slot))
+
+    def detect_ground_patch(self, size, i, j, slot=0):
+        _check(self._l.gg_detect_ground_patch(self._h, slot, size, i, j))
+
+    def spiral_ground_interpolation(self, base_z, slot=0):
+        _check(self._l.gg_spiral_ground_interpolation(self._h, slot, float(base_z)))
+
+    def interpolate_cell(self, x, y, slot=0):
+        _check(self._l.gg_interpolate_cell(self._h, slot, x, y))
 
     def eval_accumulate(self, slot=0):
         _check(self._l.gg_eval_accumulate(self._h, slot))

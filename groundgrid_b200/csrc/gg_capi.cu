@@ -1,6 +1,7 @@
 // C-ABI of groundgrid_b200 (include/groundgrid_b200.h): handle management, device arena,
 // parameter staging, stream pipeline.  All compute happens in gg_kernels.cu; there is no CPU
 // fallback -- without a usable sm_100 device every compute call returns GG_E_CUDA.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -303,11 +304,16 @@ struct gg_handle_s {
     int ring_pos = 0;
     uint64_t launches = 0;
     std::vector<void*> dev_allocs;
+    std::vector<unsigned char> seen_scratch;  // duplicate-slot check of the batch calls
     int sched_levels = 0, sched_visits = 0, sched_max = 0;
     bool out_cloud_ready = false;
-    unsigned char* d_raw = nullptr;  // f1: device copy of a PointCloud2 payload
-    size_t d_raw_cap = 0;
+    // f1: device copy of a PointCloud2 payload, one buffer per stream group (the copy and the unpack kernel of a slot
+    // run on the slot's stream; stream order then keeps two slots of one group from overwriting each other's payload)
+    unsigned char* d_raw[kStreams] = {};
+    size_t d_raw_cap[kStreams] = {};
     float* d_image = nullptr;        // f3: terrain image staging (N * N * 3)
+    unsigned char* d_image_u8 = nullptr;  // f3: 8-bit layer image staging (N * N)
+    float* d_minmax = nullptr;       //     and its min / max keys
     unsigned long long* d_eval = nullptr;  // f4: [EVAL_LABELS][2] tallies
     HostPacker* packer = nullptr;    // created on the first packed batch call
     // gg_filter_cloud_batch[_begin] alternates between two sets of input / label buffers ("parity"), so the
@@ -329,6 +335,8 @@ struct gg_handle_s {
     int n_copy_in = 4;                                   // GG_COPY_STREAMS
     int main_help = 1;                                   // GG_MAIN_HELP
     float4* detect_tab = nullptr;  // per-cell constants of the patch detection, rebuilt by gg_set_config
+    CUtensorMap layer_map{};        // TMA descriptor of the layer arena (k_detect_tma); valid iff have_layer_map
+    bool have_layer_map = false;
     bool inputs_busy = false;  // asynchronous work that reads or writes the slots' input buffers may be in flight
     std::vector<cudaEvent_t> batch_ev;                    // unit hand-over events of gg_filter_cloud_batch
     cudaEvent_t raw_ev[8] = {};      // throttle of the raw copies issued by the mixing loop
@@ -444,9 +452,12 @@ int run_scans_grouped(gg_handle h, int count, const gg_scan_desc* scans, int sto
     if (count <= 0) return GG_OK;
     if (count > h->n_slots) return fail(GG_E_ARG, "count %d exceeds the number of slots %d", count, h->n_slots);
     int rc;
+    std::vector<unsigned char>& seen = h->seen_scratch;
+    seen.assign((size_t)h->n_slots, 0);
     for (int i = 0; i < count; ++i) {
         const gg_scan_desc& d = scans[i];
         if ((rc = check_slot(h, d.slot))) return rc;
+        if (seen[d.slot]++) return fail(GG_E_ARG, "slot %d appears twice in one batch (scans of a batch run concurrently)", d.slot);
         if (!h->slots[d.slot].have_map) return fail(GG_E_STATE, "slot %d: map not initialised", d.slot);
         if (d.n_points > h->pcap) return fail(GG_E_ARG, "slot %d: %zu points exceed capacity %zu", d.slot, d.n_points, h->pcap);
     }
@@ -474,11 +485,38 @@ int run_scans_grouped(gg_handle h, int count, const gg_scan_desc* scans, int sto
         if (m == 0) continue;
         cudaStream_t st = h->streams[g];
         if ((rc = ring_commit(h, pos, m, st))) return rc;
-        h->launches += gg::launch_scan_pipeline(view, dp, m, max_points, stop_after, st, h->prof);
+        h->launches += gg::launch_scan_pipeline(view, dp, m, max_points, stop_after, st, h->prof, h->have_layer_map ? &h->layer_map : nullptr);
         GG_CUDA(cudaGetLastError());
         if ((rc = ring_release(h, pos, st))) return rc;
     }
     return GG_OK;
+}
+
+// TMA descriptor of the layer arena seen as a 3-D fp32 tensor (i fastest, j, plane = slot * n_layers + layer), box
+// 40 x 12 x 1 = the halo tile of k_detect_tma (the box starts at i0 - 4: TMA wants a 16-byte aligned innermost start).  cuTensorMapEncodeTiled is a driver-API call; it is resolved through the
+// runtime (cudaGetDriverEntryPoint) so that the library needs no link-time libcuda.  Row pitch must be a multiple of
+// 16 bytes: maps with N % 4 != 0 keep the plain-load kernel.  GG_DETECT_TMA=0 forces that kernel too.
+bool encode_layer_map(gg_handle h) {
+    const gg::View& v = h->view;
+    if (v.k.N % 4 != 0) return false;
+    if (const char* e = getenv("GG_DETECT_TMA"))
+        if (atoi(e) == 0) return false;
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return false;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)v.k.N, (cuuint64_t)v.k.N, (cuuint64_t)h->n_slots * (cuuint64_t)v.n_layers};
+    const cuuint64_t strides[2] = {(cuuint64_t)v.k.N * sizeof(float), (cuuint64_t)v.k.N2 * sizeof(float)};
+    const cuuint32_t box[3] = {40u, 12u, 1u};   // DT_WT x DT_R of k_detect_tma
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = reinterpret_cast<EncodeFn>(fn)(&h->layer_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, v.layers, dims, strides, box, estr,
+                                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
 }
 
 int ensure_out_cloud(gg_handle h) {
@@ -540,6 +578,7 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
     if (!out) return fail(GG_E_ARG, "null out pointer");
     *out = nullptr;
     if (n_slots <= 0 || max_points == 0 || !(resolution > 0.f) || !(dimension_m > 0.0)) return fail(GG_E_ARG, "bad geometry / sizes");
+    if (max_points > (1u << 26) - 256) return fail(GG_E_ARG, "max_points above 2^26 per cloud is not supported");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
         return fail(GG_E_CUDA, "no CUDA device available (groundgrid_b200 has no CPU fallback)");
@@ -571,14 +610,7 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
     const size_t N2 = (size_t)v.k.N2;
     v.n_layers = (flags & GG_FLAG_FULL_LAYERS) ? gg::L_NUM : gg::L_NUM_LIVE;
     v.pcap = h->pcap;
-    v.sort_blocks = (int)((h->pcap + gg::SORT_TILE - 1) / gg::SORT_TILE);
     v.out_blocks = (int)((h->pcap + gg::OUT_TILE - 1) / gg::OUT_TILE);
-    int bits = 1;
-    while ((1u << bits) < (unsigned)(N2 + 1)) ++bits;  // keys are cell ids in [0, N2] (N2 = "not rasterised")
-    v.key_bits = bits;
-    v.bits_lo = (bits + 1) / 2;
-    v.bits_hi = bits - v.bits_lo;
-    const int bits_max = std::max(v.bits_lo, v.bits_hi);
 
 #define GG_TRY(expr)            \
     do {                        \
@@ -599,30 +631,34 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
 
     const size_t S = (size_t)n_slots, P = h->pcap;
     GG_TRY(dev_alloc(h, &v.layers, S * v.n_layers * N2));
+    h->have_layer_map = encode_layer_map(h);
     float* expected = nullptr;
     GG_TRY(dev_alloc(h, &expected, N2));
     v.expected = expected;
     GG_TRY(dev_alloc(h, &h->detect_tab, N2));
     v.detect_tab = h->detect_tab;
     GG_TRY(dev_alloc(h, &v.points, S * P));
-    GG_TRY(dev_alloc(h, &v.kz, S * P));
-    GG_TRY(dev_alloc(h, &v.kz2, S * P));
+    GG_TRY(dev_alloc(h, &v.zw, S * P));
     GG_TRY(dev_alloc(h, &v.zsorted, S * P));
+    GG_TRY(dev_alloc(h, &v.runj, S * P));
+    GG_TRY(dev_alloc(h, &v.rundir, S * P));
     GG_TRY(dev_alloc(h, &v.dist, S * P));
     GG_TRY(dev_alloc(h, &v.code, S * P));
     GG_TRY(dev_alloc(h, &v.labels, S * P));
-    GG_TRY(dev_alloc(h, &v.cnt_i, S * N2));
+    GG_TRY(dev_alloc(h, &v.cnt64, S * N2));
     GG_TRY(dev_alloc(h, &v.raw_i, (flags & GG_FLAG_FULL_LAYERS) ? S * N2 : 1));
     GG_TRY(dev_alloc(h, &v.cellstart, S * N2));
-    GG_TRY(dev_alloc(h, &v.sort_hist, S * ((size_t)v.sort_blocks << bits_max)));
-    GG_TRY(dev_alloc(h, &v.sort_hist2, S * ((size_t)v.sort_blocks << bits_max)));
+    GG_TRY(dev_alloc(h, &v.worklist, S * N2));
+    GG_TRY(dev_alloc(h, &v.wl_count, 2 * S));
+    v.cell_tiles = (int)((N2 + 4095) / 4096);
+    GG_TRY(dev_alloc(h, &v.cell_agg, S * v.cell_tiles * 65));
     GG_TRY(dev_alloc(h, &v.out_index, S * P));
     GG_TRY(dev_alloc(h, &v.out_counts, S * (3 * (size_t)v.out_blocks + 1)));
     GG_TRY(dev_alloc(h, &v.roll_scratch, S * 2 * N2));
     v.out_cloud = nullptr;
     GG_CUDA_TRY(cudaMemset(v.layers, 0, S * v.n_layers * N2 * sizeof(float)));
     // per-cell counters are zero between scans (k_cell_stats resets what it consumed)
-    GG_CUDA_TRY(cudaMemset(v.cnt_i, 0, S * N2 * sizeof(int)));
+    GG_CUDA_TRY(cudaMemset(v.cnt64, 0, S * N2 * sizeof(unsigned long long)));
     if (flags & GG_FLAG_FULL_LAYERS) GG_CUDA_TRY(cudaMemset(v.raw_i, 0, S * N2 * sizeof(int)));
 
     // expectedPoints table (host libm, like the reference) and the spiral wavefront schedule
@@ -820,7 +856,8 @@ int gg_destroy(gg_handle h) {
     cudaDeviceSynchronize();
     delete h->prof;
     delete h->packer;
-    if (h->d_raw) cudaFree(h->d_raw);
+    for (int g = 0; g < kStreams; ++g)
+        if (h->d_raw[g]) cudaFree(h->d_raw[g]);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     for (cudaEvent_t e : h->slot_ev) cudaEventDestroy(e);
     for (int e = 0; e < 2; ++e)
@@ -894,8 +931,11 @@ int gg_update_pose_batch(gg_handle h, int count, const int* slots, const double*
     if (count > h->n_slots) return fail(GG_E_ARG, "count exceeds slots");
     GG_CUDA(cudaSetDevice(h->device));
     int rc;
+    std::vector<unsigned char>& seen = h->seen_scratch;
+    seen.assign((size_t)h->n_slots, 0);
     for (int i = 0; i < count; ++i) {
         if ((rc = check_slot(h, slots[i]))) return rc;
+        if (seen[slots[i]]++) return fail(GG_E_ARG, "slot %d appears twice in one batch", slots[i]);
         if (!h->slots[slots[i]].have_map) return fail(GG_E_STATE, "slot %d: map not initialised", slots[i]);
     }
     for (int g = 0; g < h->n_streams; ++g) {
@@ -999,18 +1039,19 @@ int gg_upload_cloud_msg(gg_handle h, int slot, const void* data, size_t n_points
     h->inputs_busy = true;
     cudaStream_t st = stream_of(h, slot);
     const size_t bytes = n_points * (size_t)point_step;
-    if (bytes > h->d_raw_cap) {
-        GG_CUDA(cudaStreamSynchronize(st));
-        if (h->d_raw) GG_CUDA(cudaFree(h->d_raw));
-        h->d_raw = nullptr;
-        h->d_raw_cap = 0;
-        GG_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_raw), bytes + 256));
-        h->d_raw_cap = bytes;
+    const int sg = stream_index(h, slot);
+    if (bytes > h->d_raw_cap[sg]) {
+        GG_CUDA(cudaStreamSynchronize(st));   // the only users of this buffer are on `st`
+        if (h->d_raw[sg]) GG_CUDA(cudaFree(h->d_raw[sg]));
+        h->d_raw[sg] = nullptr;
+        h->d_raw_cap[sg] = 0;
+        GG_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_raw[sg]), bytes + 256));
+        h->d_raw_cap[sg] = bytes;
     }
-    if (bytes) GG_CUDA(cudaMemcpyAsync(h->d_raw, data, bytes, cudaMemcpyHostToDevice, st));
+    if (bytes) GG_CUDA(cudaMemcpyAsync(h->d_raw[sg], data, bytes, cudaMemcpyHostToDevice, st));
     gg::UnpackDesc d;
     std::memset(&d, 0, sizeof(d));
-    d.raw = h->d_raw;
+    d.raw = h->d_raw[sg];
     d.dst = h->view.points + (size_t)slot * h->pcap;
     d.n = (int)n_points;
     d.point_step = point_step;
@@ -1035,6 +1076,117 @@ int gg_terrain_image(gg_handle h, int slot, float* dst) {
     h->launches += gg::launch_terrain_image(h->view, slot, h->d_image, st, h->prof);
     GG_CUDA(cudaGetLastError());
     GG_CUDA(cudaMemcpyAsync(dst, h->d_image, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    GG_CUDA(cudaStreamSynchronize(st));
+    return GG_OK;
+}
+
+// f3: the single-channel 8-bit image cv::applyColorMap receives (GroundGridNodelet.cpp:238-245)
+int gg_layer_image_u8(gg_handle h, int slot, const char* name, uint8_t* dst, float* lower, float* upper) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    if (!name || !dst) return fail(GG_E_ARG, "null argument");
+    int l = 0;
+    if ((rc = layer_index(h, slot, name, &l))) return rc;
+    GG_CUDA(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->view.k.N2;
+    if (!h->d_image_u8) {
+        if ((rc = dev_alloc(h, &h->d_image_u8, n))) return rc;
+        if ((rc = dev_alloc(h, &h->d_minmax, 2))) return rc;
+    }
+    cudaStream_t st = stream_of(h, slot);
+    const int init[2] = {0x7f800000, (int)(0xff800000u ^ 0x7fffffffu)};   // ordered keys of +inf / -inf
+    GG_CUDA(cudaMemcpyAsync(h->d_minmax, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    h->launches += gg::launch_layer_image_u8(h->view, h->view.layer(slot, l), h->d_minmax, h->d_image_u8, st);
+    GG_CUDA(cudaGetLastError());
+    int keys[2];
+    GG_CUDA(cudaMemcpyAsync(dst, h->d_image_u8, n, cudaMemcpyDeviceToHost, st));
+    GG_CUDA(cudaMemcpyAsync(keys, h->d_minmax, sizeof(keys), cudaMemcpyDeviceToHost, st));
+    GG_CUDA(cudaStreamSynchronize(st));
+    auto unkey = [](int k) { const int b = k >= 0 ? k : (k ^ 0x7fffffff); float f; std::memcpy(&f, &b, 4); return f; };
+    if (lower) *lower = unkey(keys[0]);
+    if (upper) *upper = unkey(keys[1]);
+    return GG_OK;
+}
+
+// ---- single phases (GroundSegmentation.h:56-62 of the reference) ------------------------------
+namespace {
+int one_slot_params(gg_handle h, int slot, double base_z, gg::SlotParams** dp_out, int* pos_out, cudaStream_t st) {
+    gg::SlotParams *hp = nullptr, *dp = nullptr;
+    int rc, pos = 0;
+    if ((rc = ring_acquire(h, &hp, &dp, &pos))) return rc;
+    gg_scan_desc d;
+    std::memset(&d, 0, sizeof(d));
+    d.slot = slot;
+    d.n_points = h->slots[slot].n_points;
+    d.base_z = base_z;
+    fill_params(h, d, hp[0], h->slots[slot].src);
+    if ((rc = ring_commit(h, pos, 1, st))) return rc;
+    *dp_out = dp;
+    *pos_out = pos;
+    return GG_OK;
+}
+}  // namespace
+
+int gg_detect_ground_patches(gg_handle h, int slot) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    if (!h->slots[slot].have_map) return fail(GG_E_STATE, "slot %d: map not initialised", slot);
+    GG_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream_of(h, slot);
+    gg::SlotParams* dp = nullptr;
+    int pos = 0;
+    if ((rc = one_slot_params(h, slot, 0.0, &dp, &pos, st))) return rc;
+    h->launches += gg::launch_detect_only(h->view, dp, 1, st, h->prof, h->have_layer_map ? &h->layer_map : nullptr);
+    GG_CUDA(cudaGetLastError());
+    return ring_release(h, pos, st);
+}
+
+int gg_spiral_ground_interpolation(gg_handle h, int slot, double base_z) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    if (!h->slots[slot].have_map) return fail(GG_E_STATE, "slot %d: map not initialised", slot);
+    GG_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream_of(h, slot);
+    gg::SlotParams* dp = nullptr;
+    int pos = 0;
+    if ((rc = one_slot_params(h, slot, base_z, &dp, &pos, st))) return rc;
+    h->launches += gg::launch_spiral_only(h->view, dp, 1, st, h->prof);
+    GG_CUDA(cudaGetLastError());
+    return ring_release(h, pos, st);
+}
+
+int gg_interpolate_cell(gg_handle h, int slot, int x, int y) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    const int N = h->view.k.N;
+    if (x < 1 || y < 1 || x >= N - 1 || y >= N - 1) return fail(GG_E_ARG, "cell (%d, %d) has no 3x3 neighbourhood", x, y);
+    GG_CUDA(cudaSetDevice(h->device));
+    h->launches += gg::launch_interpolate_cell(h->view, slot, x, y, stream_of(h, slot));
+    GG_CUDA(cudaGetLastError());
+    return GG_OK;
+}
+
+int gg_detect_ground_patch(gg_handle h, int slot, int patch_size, int i, int j) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    if (patch_size != 3 && patch_size != 5) return fail(GG_E_ARG, "patch size must be 3 or 5");
+    const int N = h->view.k.N, H = patch_size / 2;
+    if (i < H || j < H || i >= N - H || j >= N - H) return fail(GG_E_ARG, "cell (%d, %d) has no %dx%d neighbourhood", i, j, patch_size, patch_size);
+    GG_CUDA(cudaSetDevice(h->device));
+    h->launches += gg::launch_detect_cell(h->view, slot, patch_size, i, j, stream_of(h, slot));
+    GG_CUDA(cudaGetLastError());
+    return GG_OK;
+}
+
+// class << 24 | cell of every input point of the slot's last rasterisation (the index lists insert_cloud fills)
+int gg_get_point_classes(gg_handle h, int slot, uint32_t* codes, size_t n) {
+    int rc = check_slot(h, slot);
+    if (rc) return rc;
+    if (n > h->slots[slot].n_points || (n && !codes)) return fail(GG_E_ARG, "bad class buffer");
+    if (!h->slots[slot].ran) return fail(GG_E_STATE, "slot %d: no rasterised scan", slot);
+    GG_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = stream_of(h, slot);
+    if (n) GG_CUDA(cudaMemcpyAsync(codes, h->view.code + (size_t)slot * h->pcap, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     GG_CUDA(cudaStreamSynchronize(st));
     return GG_OK;
 }
@@ -1111,7 +1263,7 @@ int gg_profile_read(gg_handle h, double* ms_per_kernel, uint32_t* launches_per_k
 int gg_profile_kernel_count(void) { return gg::K_NUM; }
 
 const char* gg_profile_kernel_name(int id) {
-    static const char* names[gg::K_NUM] = {"k_rasterize",   "k_scan_lo_cells", "k_sort_scatter(lo)", "k_sort_scan(hi)", "k_sort_scatter(hi)",
+    static const char* names[gg::K_NUM] = {"k_rasterize",   "k_cell_tiles",    "k_cell_place",    "k_scatter",
                                            "k_cell_stats",  "k_detect",        "k_spiral",           "k_label",         "k_roll_gather",
                                            "k_roll_commit", "k_out_count",     "k_out_scan",         "k_out_write",     "k_unpack_transform",
                                            "k_terrain_image", "k_eval_counts"};
@@ -1220,9 +1372,11 @@ int gg_filter_cloud_batch_begin(gg_handle h, int count, const gg_scan_desc* scan
     if (count > h->n_slots) return fail(GG_E_ARG, "count exceeds slots");
     GG_CUDA(cudaSetDevice(h->device));
     int rc;
+    std::vector<unsigned char> seen((size_t)h->n_slots, 0);   // (run_scans_grouped re-checks its own sub-batches with the handle's scratch)
     for (int i = 0; i < count; ++i) {
         const gg_scan_desc& d = scans[i];
         if ((rc = check_slot(h, d.slot))) return rc;
+        if (seen[d.slot]++) return fail(GG_E_ARG, "slot %d appears twice in one batch (scans of a batch run concurrently)", d.slot);
         if (d.n_points > h->pcap) return fail(GG_E_ARG, "slot %d: too many points", d.slot);
         if (d.n_points && !points[i]) return fail(GG_E_ARG, "scan %d: null cloud", i);
         if (!h->slots[d.slot].have_map) return fail(GG_E_STATE, "slot %d: map not initialised", d.slot);

@@ -1,6 +1,7 @@
 // Internal definitions shared by the kernels (gg_kernels.cu) and the C-ABI (gg_capi.cu).
 // Not installed; the public boundary is include/groundgrid_b200.h.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -111,25 +112,26 @@ struct View {
     const float4* detect_tab;  // [N2] per-cell constants of the patch detection (gg_kernels.cu:k_build_detect_table)
     gg_point* points;     // [n_slots][pcap]
     unsigned char* packed;  // [n_slots][14 * pcap] packed clouds (allocated on first use)
-    uint2* kz;            // [n_slots][pcap] (sort key, z bits) per input point: key = cell index of kept points, N2 for everything else
-    uint2* kz2;           // sort ping-pong (after the low-digit pass)
-    float* zsorted;       // [n_slots][pcap] z of kept points grouped by cell, input order inside a cell
+    uint2* zw;            // [n_slots][pcap] per input point: (z bits, position in the cell's segment | run-head flag << 31)
+    uint32_t* runj;       // [n_slots][pcap] run heads only: arrival number of the run in its cell | (run length - 1) << 26
+    float* zsorted;       // [n_slots][pcap] z of kept points grouped by cell: the cell's segment is a sequence of runs
+    uint2* rundir;        // [n_slots][pcap] run directory, cell by cell at cellstart: (run id = point index >> 5, first position | (length - 1) << 26)
     float* dist;          // [n_slots][pcap] hypotf(x - ox, y - oy)
     uint32_t* code;       // [n_slots][pcap] class << 24 | cell
     uint8_t* labels;      // [n_slots][pcap]
-    int* cnt_i;           // [n_slots][N2] kept points per cell
+    unsigned long long* cnt64;  // [n_slots][N2] runs of the cell << 32 | kept points of the cell (one atomic per run)
     int* raw_i;           // [n_slots][N2] inside points per cell (full layers)
-    int* cellstart;       // [n_slots][N2] exclusive scan of cnt_i
-    int* sort_hist;       // [n_slots][digits * sort_blocks] pass 1 (low digit): per-tile histogram -> offsets
-    int* sort_hist2;      // same for pass 2 (high digit); filled by the pass-1 scatter with atomics
+    int* cellstart;       // [n_slots][N2] exclusive scan of the per-cell point counts
+    int* worklist;        // [n_slots][N2] non-empty cells grouped by count class, heaviest first (k_scan_cells)
+    int* wl_count;        // [n_slots][2] entries of the worklist, kept points of the scan
+    int* cell_agg;        // [n_slots][cell_tiles][65] per tile of 4096 cells: cells per count class, kept points
+    int cell_tiles;       // ceil(N2 / 4096)
     uint32_t* out_index;  // [n_slots][pcap]
     int* out_counts;      // [n_slots][3 * out_blocks + 1]  (+1: n_out)
     gg_point* out_cloud;  // [n_slots][pcap] (allocated lazily)
     float* roll_scratch;  // [n_slots][2][N2]
     size_t pcap;
-    int sort_blocks;      // ceil(pcap / SORT_TILE)
     int out_blocks;       // ceil(pcap / OUT_TILE)
-    int key_bits, bits_lo, bits_hi;
     // spiral wavefront schedule (shared by all slots)
     const int* level_start;   // [levels + 1]
     const uint32_t* visits;   // [n_visits]  x | y << 16
@@ -143,13 +145,13 @@ struct View {
     __host__ __device__ float* layer(int slot, int l) const { return layers + ((size_t)slot * n_layers + l) * k.N2; }
 };
 
-constexpr int SORT_TILE = 2048;
-constexpr int SORT_THREADS = 256;
+constexpr int RASTER_TILE = 2048;
+constexpr int RASTER_THREADS = 256;
 constexpr int OUT_TILE = 1024;
 
 // kernels of the pipeline, as reported by the profiling hooks (gg_profile_read)
 enum KernelId : int {
-    K_RASTERIZE = 0, K_SCAN_LO_CELLS, K_SORT_SCATTER1, K_SORT_SCAN2, K_SORT_SCATTER2, K_CELL_STATS, K_DETECT, K_SPIRAL, K_LABEL, K_ROLL_GATHER, K_ROLL_COMMIT, K_OUT_COUNT, K_OUT_SCAN,
+    K_RASTERIZE = 0, K_CELL_TILES, K_CELL_PLACE, K_SCATTER, K_CELL_STATS, K_DETECT, K_SPIRAL, K_LABEL, K_ROLL_GATHER, K_ROLL_COMMIT, K_OUT_COUNT, K_OUT_SCAN,
     K_OUT_WRITE, K_UNPACK, K_TERRAIN, K_EVAL, K_NUM
 };
 
@@ -166,8 +168,15 @@ struct Profiler {
 int launch_init_map(const View& v, int slot, float z, cudaStream_t st);
 int launch_build_detect_table(const View& v, float4* tab, cudaStream_t st);
 int launch_roll(const View& v, const SlotParams* batch, int count, cudaStream_t st, Profiler* prof);
+// layer_map: TMA descriptor of the handle's layer arena as a 3-D tensor (i, j, slot * n_layers + layer), box
+// 40 x 12 x 1 (k_detect_tma); null -> the patch detection stages its tile with plain loads (N % 4 != 0)
 int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int max_points, int stop_after, cudaStream_t st,
-                         Profiler* prof);
+                         Profiler* prof, const CUtensorMap* layer_map);
+// single phases / single cells (the reference's public per-phase methods)
+int launch_detect_only(const View& v, const SlotParams* batch, int count, cudaStream_t st, Profiler* prof, const CUtensorMap* layer_map);
+int launch_spiral_only(const View& v, const SlotParams* batch, int count, cudaStream_t st, Profiler* prof);
+int launch_interpolate_cell(const View& v, int slot, int x, int y, cudaStream_t st);
+int launch_detect_cell(const View& v, int slot, int S, int i, int j, cudaStream_t st);
 int launch_output(const View& v, const SlotParams* batch, int count, int max_points, bool want_cloud, cudaStream_t st,
                   Profiler* prof);
 // "next" rows of SURVEY.md section 8(f)
@@ -181,6 +190,8 @@ struct UnpackDesc {   // f1: PointCloud2 payload -> PointXYZIR records in the ma
 };
 int launch_unpack(const UnpackDesc& d, cudaStream_t st, Profiler* prof);
 int launch_terrain_image(const View& v, int slot, float* dst, cudaStream_t st, Profiler* prof);
+// mm: 2 floats (ordered-int keys of min / max), preset by the caller to the keys of +inf / -inf; dst: N * N bytes, row-major (i, j)
+int launch_layer_image_u8(const View& v, const float* layer, float* mm, unsigned char* dst, cudaStream_t st);
 int launch_eval(const View& v, const SlotParams* batch, unsigned long long* counts, cudaStream_t st, Profiler* prof);
 constexpr int EVAL_LABELS = 1024;  // ring values (SemanticKITTI label ids <= 259) x {ground, non-ground}
 

@@ -1,10 +1,13 @@
 // groundgrid_b200 -- hand-written sm_100a kernels of the GroundGrid per-scan hot path.
 //
 // Phases (reference: src/GroundSegmentation.cpp, see DESIGN.md for the data layout):
-//   k_rasterize     point -> cell, ignore test, outlier ray-march            (:200-280)
-//   k_sort_*        stable LSD radix sort of kept points by cell (input order kept inside a
-//                   cell, because the Welford recurrence of :298-305 is order dependent)
-//   k_cell_stats    per-cell sequential count / min / Welford mean+M2 -> variance (:282-309,323)
+//   k_rasterize     point -> cell, ignore test, outlier ray-march; every warp claims, per cell it
+//                   touches, one contiguous run of the cell's segment (one atomic per run)     (:200-280)
+//   k_cell_tiles/place  exclusive scan of the per-cell counts -> segment starts; worklist of non-empty cells by count class
+//   k_scatter       z of every kept point -> its slot of the cell's segment, run descriptors
+//   k_cell_stats    per-cell sequential count / min / Welford mean+M2 -> variance, walking the
+//                   runs of a cell in input order (the Welford recurrence of :298-305 is order
+//                   dependent)                                                                 (:282-309,323)
 //   k_detect        3x3 / 5x5 ground-patch stencil updating G, C              (:314-395)
 //   k_spiral        level-scheduled wavefront of the in-place spiral sweep    (:398-465)
 //   k_label         per-point ground / non-ground decision                    (:146-196)
@@ -15,7 +18,10 @@
 // written with __f*_rn intrinsics where a product feeds a sum), IEEE division / sqrt,
 // fp64 wherever the reference's C++ promotes to double, Eigen 3.3.7's binary-split
 // reduction order for every fixed-size block sum.
+#include <cuda.h>   // CUtensorMap (the descriptor is encoded on the host, gg_capi.cu)
+
 #include <cfloat>
+#include <cstddef>
 #include <cstdio>
 
 #include "gg_internal.h"
@@ -93,6 +99,7 @@ __device__ __forceinline__ int warp_inclusive_scan(int v) {
 // Exclusive scan of n ints (in -> out, may alias) by one block of 1024 threads: tiles of 4096
 // elements, 4 consecutive ints per thread (coalesced), next tile prefetched while the current
 // one is scanned.  Returns the grand total to every thread.
+template <int STRIDE = 1>
 __device__ int block_exclusive_scan_1024(const int* in, int* out, int n) {
     __shared__ int s_warp[32];
     __shared__ int s_carry;
@@ -101,7 +108,7 @@ __device__ int block_exclusive_scan_1024(const int* in, int* out, int n) {
     if (tid == 0) s_carry = 0;
     int nx[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) nx[q] = (tid * 4 + q < n) ? in[tid * 4 + q] : 0;
+    for (int q = 0; q < 4; ++q) nx[q] = (tid * 4 + q < n) ? in[(size_t)(tid * 4 + q) * STRIDE] : 0;
     __syncthreads();
     for (int base = 0; base < n; base += 4096) {
         int cur[4];
@@ -109,7 +116,7 @@ __device__ int block_exclusive_scan_1024(const int* in, int* out, int n) {
         for (int q = 0; q < 4; ++q) cur[q] = nx[q];
         const int nb = base + 4096 + tid * 4;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) nx[q] = (nb + q < n) ? in[nb + q] : 0;
+        for (int q = 0; q < 4; ++q) nx[q] = (nb + q < n) ? in[(size_t)(nb + q) * STRIDE] : 0;
         const int sum = cur[0] + cur[1] + cur[2] + cur[3];
         const int incl = warp_inclusive_scan(sum);
         if (lane == 31) s_warp[warp] = incl;
@@ -222,7 +229,7 @@ __global__ void __launch_bounds__(256) k_roll_commit(View v, const SlotParams* _
 // ------------------------------------------------------------------------------------------
 // phase 1a: per-point rasterisation front end (insert_cloud up to the accumulate step)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t rasterize_point(const View& v, const SlotParams& sp, int i) {
+__device__ __forceinline__ uint32_t rasterize_point(const View& v, const SlotParams& sp, int i, float& zout) {
     const Const& k = v.k;
     const int N = k.N;
     const size_t base = (size_t)sp.slot * v.pcap;
@@ -305,148 +312,229 @@ __device__ __forceinline__ uint32_t rasterize_point(const View& v, const SlotPar
             } else {
                 key = (uint32_t)cell;
                 code = ((border ? PC_KEPT_BORDER : PC_KEPT) << 24) | (uint32_t)cell;
-                atomicAdd(v.cnt_i + (size_t)sp.slot * k.N2 + cell, 1);
             }
         }
     }
-    v.kz[base + i] = make_uint2(key, __float_as_uint(z));  // one 8-byte element travels through the sort
     v.code[base + i] = code;
+    zout = z;
     return key;
 }
 
-// One block = one sort tile (SORT_TILE consecutive points, SORT_THREADS threads): besides the
-// per-point products it leaves the tile's histogram of the LOW key digit (pass 1 of the radix sort
-// needs no separate counting pass) and clears its column of the high-digit table.
+// Words that travel from k_rasterize to k_scatter:
+//   zw[i]   = (z bits, position inside the cell's segment | run-head flag in bit 31)      every point
+//   runj[i] = arrival number of the run among the cell's runs | (run length - 1) << 26     run heads only
+constexpr uint32_t RUN_LOW26 = (1u << 26) - 1u;
+
+// RASTER_TILE consecutive points per block, RASTER_THREADS threads, thread order == point order inside a round, so
+// the 32 lanes of a warp always hold 32 CONSECUTIVE points (point index >> 5 is warp-uniform: the "run id").
+// Kept points of a warp that fall into the same cell form one run: the lowest lane claims `len` consecutive
+// positions of the cell's segment and the run's directory entry with ONE 64-bit atomicAdd (low word: points of the
+// cell, high word: runs of the cell); lane order inside the run is input order.  Runs of one cell never interleave
+// (different warps own disjoint index ranges), so input order inside a cell = runs sorted by run id -- which
+// k_cell_stats restores from the (few) directory entries without any sort pass over the points.
 template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) k_rasterize(View v, const SlotParams* __restrict__ batch, int nb) {
-    extern __shared__ int s_hist[];
+__global__ void __launch_bounds__(RASTER_THREADS, MIN_BLOCKS) k_rasterize(View v, const SlotParams* __restrict__ batch) {
     const SlotParams& sp = batch[blockIdx.y];
-    const int D = 1 << v.bits_lo, D2 = 1 << v.bits_hi;
-    for (int d = threadIdx.x; d < D; d += SORT_THREADS) s_hist[d] = 0;
-    __syncthreads();
     const int n = sp.n_points;
-    const int tile0 = blockIdx.x * SORT_TILE;
-    const uint32_t mask = (uint32_t)D - 1u;
-    for (int r = 0; r < SORT_TILE / SORT_THREADS; ++r) {
-        const int i = tile0 + r * SORT_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&s_hist[rasterize_point(v, sp, i) & mask], 1);
-    }
-    __syncthreads();
-    const size_t hoff = (size_t)sp.slot * ((size_t)v.sort_blocks << max(v.bits_lo, v.bits_hi));
-    int* hist = v.sort_hist + hoff;
-    for (int d = threadIdx.x; d < D; d += SORT_THREADS) hist[d * nb + blockIdx.x] = s_hist[d];
-    int* hist2 = v.sort_hist2 + hoff;
-    for (int d = threadIdx.x; d < D2; d += SORT_THREADS) hist2[d * nb + blockIdx.x] = 0;
-}
-
-// ------------------------------------------------------------------------------------------
-// phase 1b: stable LSD radix sort (cell -> z), two passes
-// ------------------------------------------------------------------------------------------
-// hist layout [slot][digit * nb + tile].  Blocks [0, count) scan the low-digit table of the sort,
-// blocks [count, 2 count) the per-cell kept counts (both only depend on k_rasterize).
-__global__ void __launch_bounds__(1024) k_scan_lo_cells(View v, const SlotParams* __restrict__ batch, int count, int nb) {
-    const bool cells = (int)blockIdx.x >= count;
-    const SlotParams& sp = batch[cells ? blockIdx.x - count : blockIdx.x];
-    if (cells) {
-        const size_t off = (size_t)sp.slot * v.k.N2;
-        block_exclusive_scan_1024(v.cnt_i + off, v.cellstart + off, v.k.N2);
-    } else {
-        int* hist = v.sort_hist + (size_t)sp.slot * ((size_t)v.sort_blocks << max(v.bits_lo, v.bits_hi));
-        block_exclusive_scan_1024(hist, hist, nb << v.bits_lo);
-    }
-}
-
-__global__ void __launch_bounds__(1024) k_sort_scan_hi(View v, const SlotParams* __restrict__ batch, int nb) {
-    const SlotParams& sp = batch[blockIdx.x];
-    int* hist = v.sort_hist2 + (size_t)sp.slot * ((size_t)v.sort_blocks << max(v.bits_lo, v.bits_hi));
-    block_exclusive_scan_1024(hist, hist, nb << v.bits_hi);
-}
-
-// Stable scatter.  A block owns SORT_TILE consecutive items and walks them in rounds of
-// SORT_THREADS (thread order == item order).  Ranks inside a round: lanes of a warp rank
-// themselves with __match_any_sync, each (warp, digit) leader posts its count in a small
-// [warps][digits] table, and a thread's rank is the running digit count of earlier rounds + the
-// counts of earlier warps + its rank inside the warp -- two barriers per round, equal digits keep
-// their input order.
-template <bool LAST, int MIN_BLOCKS>
-__global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) k_sort_scatter(View v, const SlotParams* __restrict__ batch, const uint2* __restrict__ kz_in,
-                                                               uint2* __restrict__ kz_out, float* __restrict__ vals_out, int shift, int bits, int nb) {
-    extern __shared__ int s_run[];  // [D] running per-digit count, then [WARPS][D] u16 counts of the current round
-    constexpr int ROUNDS = SORT_TILE / SORT_THREADS;
-    constexpr int WARPS = SORT_THREADS / 32;
-    const SlotParams& sp = batch[blockIdx.y];
-    const int D = 1 << bits;
-    unsigned short* s_wc = reinterpret_cast<unsigned short*>(s_run + D);
-    for (int d = threadIdx.x; d < D; d += SORT_THREADS) s_run[d] = 0;
-    for (int d = threadIdx.x; d < WARPS * D / 2; d += SORT_THREADS) reinterpret_cast<int*>(s_wc)[d] = 0;
-    __syncthreads();
-    const int n = sp.n_points;
+    const int tile0 = blockIdx.x * RASTER_TILE;
+    if (tile0 >= n) return;
     const size_t base = (size_t)sp.slot * v.pcap;
-    const uint2* kin = kz_in + base;
-    const int tile0 = blockIdx.x * SORT_TILE;
-    const uint32_t mask = (uint32_t)D - 1u;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long* cnt = v.cnt64 + (size_t)sp.slot * v.k.N2;
+    const int lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int r = 0; r < RASTER_TILE / RASTER_THREADS; ++r) {
+        const int i = tile0 + r * RASTER_THREADS + threadIdx.x;
+        if (__all_sync(0xffffffffu, i >= n)) break;
+        uint32_t key = (uint32_t)v.k.N2;
+        float z = 0.0f;
+        if (i < n) key = rasterize_point(v, sp, i, z);
+        const bool kept = key != (uint32_t)v.k.N2;
+        // lanes without a kept point get a private pseudo key (never equal to a cell id)
+        const uint32_t peers = __match_any_sync(0xffffffffu, kept ? key : (0x80000000u | (uint32_t)lane));
+        const int leader = __ffs(peers) - 1;
+        const int len = __popc(peers);
+        const bool head = kept && lane == leader;
+        unsigned long long old = 0ull;
+        if (head) old = atomicAdd(cnt + key, (1ull << 32) | (unsigned long long)len);
+        const int start = __shfl_sync(0xffffffffu, (int)(uint32_t)old, leader);
+        if (i < n) {
+            const uint32_t w = kept ? ((uint32_t)(start + __popc(peers & lt_mask)) | (head ? 0x80000000u : 0u)) : 0u;
+            v.zw[base + i] = make_uint2(__float_as_uint(z), w);
+            if (head) v.runj[base + i] = ((uint32_t)(old >> 32) & RUN_LOW26) | ((uint32_t)(len - 1) << 26);
+        }
+    }
+}
 
-    uint32_t my_key[ROUNDS];
-    float my_val[ROUNDS];
-    int my_rank[ROUNDS];
+// ------------------------------------------------------------------------------------------
+// phase 1b: segment starts (exclusive scan of the per-cell point counts), then every kept z goes to its
+// position and every run head files the run in the cell's directory
+// ------------------------------------------------------------------------------------------
+// Count classes of the cell worklist: exact up to 32 points, then steps of 1/4 octave (cells of one class differ by
+// less than 20 % in their walk length); heaviest class first.
+constexpr int WL_CLASSES = 64;
+__device__ __forceinline__ int worklist_class(int c) {
+    if (c <= 32) return c;                                  // 1 .. 32 exact (0 never enters the list)
+    const int e = 31 - __clz(c);                            // floor(log2 c) >= 5
+    const int q = (c >> (e - 2)) & 3;                       // two bits below the leading one
+    const int k = 33 + (e - 5) * 4 + q;
+    return k < WL_CLASSES ? k : WL_CLASSES - 1;
+}
+
+// Segment starts and worklist in two short, fully parallel launches over tiles of CELL_TILE cells (a single block
+// per scan would be a long serial chain):
+//   k_cell_tiles   per tile: kept points and cells per count class            -> cell_agg[scan][tile][0 .. WL_CLASSES]
+//   k_cell_place   per tile: prefix over the earlier tiles' aggregates, local exclusive scan -> cellstart; every
+//                  non-empty cell goes to the scan's worklist, grouped by class (heaviest class first) so that the 32
+//                  cells a warp of k_cell_stats walks have (almost) the same length.  The order inside a class is
+//                  arbitrary -- every cell's result is independent of it.
+constexpr int CELL_TILE = 4096;      // CT_THREADS threads x CT_PER cells
+constexpr int CT_THREADS = 256, CT_PER = 16;
+constexpr int AGG_STRIDE = WL_CLASSES + 1;   // [0, WL_CLASSES): cells per class, [WL_CLASSES]: kept points
+
+// 16 consecutive cells per thread: eight 16-byte loads of the (runs << 32 | points) counters, low words kept
+__device__ __forceinline__ void load_tile_counts(const unsigned long long* cnt64, int N2, int cell0, int c[CT_PER]) {
+    if (cell0 + CT_PER <= N2 && (((size_t)cnt64 & 15) == 0) && (cell0 & 1) == 0) {
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(cnt64 + cell0);
 #pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) {
-        const int idx = tile0 + r * SORT_THREADS + threadIdx.x;
-        const bool valid = idx < n;
-        const uint2 e = valid ? kin[idx] : make_uint2(0u, 0u);
-        my_key[r] = e.x;
-        my_val[r] = __uint_as_float(e.y);
-    }
-#pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) {
-        const int idx = tile0 + r * SORT_THREADS + threadIdx.x;
-        const bool valid = idx < n;
-        const int d = valid ? (int)((my_key[r] >> shift) & mask) : D;  // D: matches only other invalid lanes
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        const int rank_in_warp = __popc(peers & lt_mask);
-        const int total = __popc(peers);
-        const bool leader = valid && rank_in_warp == 0;
-        if (leader) s_wc[warp * D + d] = (unsigned short)total;
-        __syncthreads();
-        int before = 0;
-        if (valid) {
-            before = s_run[d];
-            for (int w = 0; w < warp; ++w) before += s_wc[w * D + d];
+        for (int q = 0; q < CT_PER / 2; ++q) {
+            const ulonglong2 v = p[q];
+            c[2 * q] = (int)(uint32_t)v.x;
+            c[2 * q + 1] = (int)(uint32_t)v.y;
         }
-        my_rank[r] = before + rank_in_warp;
-        __syncthreads();
-        if (leader) {
-            atomicAdd(&s_run[d], total);
-            s_wc[warp * D + d] = 0;
-        }
-        __syncwarp();
-    }
-    const size_t hoff = (size_t)sp.slot * ((size_t)v.sort_blocks << max(v.bits_lo, v.bits_hi));
-    const int* __restrict__ offs = (LAST ? v.sort_hist2 : v.sort_hist) + hoff;
-    int* hist2 = v.sort_hist2 + hoff;
-    // fetch all tile offsets first (read-only path: the table is not written by this kernel), so that
-    // the eight L2 latencies overlap instead of serialising behind the stores / atomics below
-    int my_off[ROUNDS];
+    } else {
 #pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) {
-        const int idx = tile0 + r * SORT_THREADS + threadIdx.x;
-        my_off[r] = idx < n ? __ldg(offs + (int)((my_key[r] >> shift) & mask) * nb + blockIdx.x) : 0;
+        for (int q = 0; q < CT_PER; ++q) c[q] = (cell0 + q < N2) ? (int)(uint32_t)cnt64[cell0 + q] : 0;
+    }
+}
+
+__global__ void __launch_bounds__(CT_THREADS) k_cell_tiles(View v, const SlotParams* __restrict__ batch) {
+    __shared__ int s_cls[AGG_STRIDE];
+    const SlotParams& sp = batch[blockIdx.y];
+    const int N2 = v.k.N2, tid = threadIdx.x, lane = tid & 31;
+    if (tid < AGG_STRIDE) s_cls[tid] = 0;
+    __syncthreads();
+    int c[CT_PER];
+    load_tile_counts(v.cnt64 + (size_t)sp.slot * N2, N2, blockIdx.x * CELL_TILE + tid * CT_PER, c);
+    int sum = 0;
+#pragma unroll
+    for (int q = 0; q < CT_PER; ++q) {
+        sum += c[q];
+        if (c[q] > 0) atomicAdd(&s_cls[worklist_class(c[q])], 1);
     }
 #pragma unroll
-    for (int r = 0; r < ROUNDS; ++r) {
-        const int idx = tile0 + r * SORT_THREADS + threadIdx.x;
-        if (idx < n) {
-            const int pos = my_off[r] + my_rank[r];
-            if (!LAST) {
-                kz_out[base + pos] = make_uint2(my_key[r], __float_as_uint(my_val[r]));
-                // histogram of the next pass: high digit x destination tile
-                atomicAdd(&hist2[(int)(my_key[r] >> bits) * nb + pos / SORT_TILE], 1);
-            } else {
-                vals_out[base + pos] = my_val[r];
+    for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if (lane == 0 && sum) atomicAdd(&s_cls[WL_CLASSES], sum);
+    __syncthreads();
+    if (tid < AGG_STRIDE) v.cell_agg[((size_t)sp.slot * v.cell_tiles + blockIdx.x) * AGG_STRIDE + tid] = s_cls[tid];
+}
+
+__global__ void __launch_bounds__(CT_THREADS) k_cell_place(View v, const SlotParams* __restrict__ batch) {
+    __shared__ int s_cur[AGG_STRIDE];   // worklist cursor of every class for this tile; [WL_CLASSES]: first segment start of the tile
+    __shared__ int s_warp[CT_THREADS / 32];
+    const SlotParams& sp = batch[blockIdx.y];
+    const int N2 = v.k.N2, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles = v.cell_tiles, tile = blockIdx.x;
+    const int* agg = v.cell_agg + (size_t)sp.slot * tiles * AGG_STRIDE;
+    const size_t off = (size_t)sp.slot * N2;
+    const int cell0 = tile * CELL_TILE + tid * CT_PER;
+    int c[CT_PER];
+    load_tile_counts(v.cnt64 + off, N2, cell0, c);
+    // one warp: per class (2 per lane) the total over all tiles and the part of the earlier tiles
+    if (warp == 0) {
+        int tot[2] = {0, 0}, pre[2] = {0, 0};
+        const int k0 = WL_CLASSES - 1 - 2 * lane, k1 = k0 - 1;   // lane 0: classes 63, 62 ... lane 31: classes 1, 0
+        for (int p = 0; p < tiles; ++p) {
+            const int a0 = agg[p * AGG_STRIDE + k0], a1 = agg[p * AGG_STRIDE + k1];
+            tot[0] += a0;
+            tot[1] += a1;
+            if (p < tile) {
+                pre[0] += a0;
+                pre[1] += a1;
             }
         }
+        const int incl = warp_inclusive_scan(tot[0] + tot[1]);   // classes in descending order: heaviest first
+        s_cur[k0] = incl - tot[0] - tot[1] + pre[0];
+        s_cur[k1] = incl - tot[1] + pre[1];
+        int pts = 0, pts_all = 0;
+        for (int p = lane; p < tiles; p += 32) {
+            const int a = agg[p * AGG_STRIDE + WL_CLASSES];
+            pts_all += a;
+            if (p < tile) pts += a;
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            pts += __shfl_xor_sync(0xffffffffu, pts, d);
+            pts_all += __shfl_xor_sync(0xffffffffu, pts_all, d);
+        }
+        if (lane == 0) s_cur[WL_CLASSES] = pts;
+        if (tile == 0 && lane == 31) {
+            v.wl_count[2 * sp.slot] = incl;          // non-empty cells of the scan
+            v.wl_count[2 * sp.slot + 1] = pts_all;   // kept points of the scan (= end of the last segment)
+        }
+    }
+    int sum = 0;
+#pragma unroll
+    for (int q = 0; q < CT_PER; ++q) sum += c[q];
+    const int incl = warp_inclusive_scan(sum);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int run = s_cur[WL_CLASSES] + incl - sum;
+    for (int w = 0; w < warp; ++w) run += s_warp[w];
+    int* wl = v.worklist + off;
+    int cs[CT_PER];
+#pragma unroll
+    for (int q = 0; q < CT_PER; ++q) {
+        cs[q] = run;
+        run += c[q];
+        if (c[q] > 0) wl[atomicAdd(&s_cur[worklist_class(c[q])], 1)] = cell0 + q;
+    }
+    if (cell0 + CT_PER <= N2 && (N2 & 3) == 0) {
+        int4* dst = reinterpret_cast<int4*>(v.cellstart + off + cell0);
+#pragma unroll
+        for (int q = 0; q < CT_PER / 4; ++q) dst[q] = make_int4(cs[4 * q], cs[4 * q + 1], cs[4 * q + 2], cs[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < CT_PER; ++q)
+            if (cell0 + q < N2) v.cellstart[off + cell0 + q] = cs[q];
+    }
+}
+
+constexpr int SCATTER_ILP = 4;
+
+// Directory entry of a run, at rundir[cellstart + arrival number] (a cell has at most as many runs as points):
+//   x = run id (point index >> 5), y = first position inside the segment | (length - 1) << 26
+__global__ void __launch_bounds__(256) k_scatter(View v, const SlotParams* __restrict__ batch) {
+    const SlotParams& sp = batch[blockIdx.y];
+    const int n = sp.n_points;
+    const int i0 = blockIdx.x * (256 * SCATTER_ILP) + threadIdx.x;
+    if (i0 >= n) return;
+    const size_t base = (size_t)sp.slot * v.pcap;
+    const int* cellstart = v.cellstart + (size_t)sp.slot * v.k.N2;
+    float* zs = v.zsorted + base;
+    uint2* dir = v.rundir + base;
+    uint32_t code[SCATTER_ILP];
+    uint2 zw[SCATTER_ILP];
+    int cs[SCATTER_ILP];
+    uint32_t jl[SCATTER_ILP];
+#pragma unroll
+    for (int u = 0; u < SCATTER_ILP; ++u) {
+        const int i = i0 + u * 256;
+        code[u] = i < n ? v.code[base + i] : (PC_ABSENT << 24);
+        zw[u] = i < n ? v.zw[base + i] : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < SCATTER_ILP; ++u) {
+        const uint32_t cls = code[u] >> 24;
+        const bool kept = cls == PC_KEPT || cls == PC_KEPT_BORDER;
+        cs[u] = kept ? cellstart[code[u] & 0xffffffu] : -1;
+        jl[u] = (kept && (zw[u].y & 0x80000000u)) ? v.runj[base + i0 + u * 256] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < SCATTER_ILP; ++u) {
+        if (cs[u] < 0) continue;
+        const uint32_t p = zw[u].y & 0x7fffffffu;
+        zs[cs[u] + (int)p] = __uint_as_float(zw[u].x);
+        if (zw[u].y & 0x80000000u) dir[cs[u] + (int)(jl[u] & RUN_LOW26)] = make_uint2((uint32_t)((i0 + u * 256) >> 5), p | (jl[u] & ~RUN_LOW26));
     }
 }
 
@@ -454,68 +542,172 @@ __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) k_sort_scatter(View 
 // phase 1c: per-cell sequential statistics (the accumulate step of insert_cloud, :282-309,
 // in input order) + variance (:323).  One thread per cell.
 // ------------------------------------------------------------------------------------------
+constexpr int CS_THREADS = 256;
+
 template <bool FULL>
-__global__ void __launch_bounds__(128) k_cell_stats(View v, const SlotParams* __restrict__ batch) {
+__global__ void __launch_bounds__(CS_THREADS, FULL ? 2 : 4) k_cell_stats(View v, const SlotParams* __restrict__ batch) {
     const SlotParams& sp = batch[blockIdx.y];
     const Const& k = v.k;
-    // a warp owns an 8 x 4 patch of cells: point density varies with the distance to the sensor, so a
-    // compact patch has far more uniform per-cell counts (= loop trip counts) than a 32 x 1 strip
-    const int wid = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    const int tiles_i = (k.N + 7) >> 3;
-    const int ci = (wid % tiles_i) * 8 + (lane & 7), cj = (wid / tiles_i) * 4 + (lane >> 3);
-    const bool live = ci < k.N && cj < k.N;
-    const int cell = live ? ci + cj * k.N : 0;
     const size_t coff = (size_t)sp.slot * k.N2;
-    const int cnt = live ? v.cnt_i[coff + cell] : 0;
-    const float* zs = v.zsorted + (size_t)sp.slot * v.pcap + (live ? v.cellstart[coff + cell] : 0);
-    const float oz = sp.oz;
-    // The eight cells of a patch row own one contiguous run of the sorted heights.  Before the (lane-strided, hence
-    // poorly coalesced) per-cell walks start, the warp touches the first lines of its four runs together, one line
-    // per lane, so that those misses overlap instead of being paid one 8-value batch at a time.
-    {
-        const unsigned long long begin = __shfl_sync(0xffffffffu, (unsigned long long)zs, lane & 24);  // column 0 of the row
-        unsigned long long end = live ? (unsigned long long)(zs + cnt) : 0ull;                             // max over the row
+    const int gt = blockIdx.x * CS_THREADS + threadIdx.x;
+    const int kept_total = v.wl_count[2 * sp.slot + 1];
+    // (1) four consecutive cells per thread, coalesced: the per-scan resets every cell needs, and the results of an
+    //     EMPTY cell (count 0, m2 / (0 + FLT_MIN) = 0, min = FLT_MAX, :61-75,323).  Empty <=> zero-length segment
+    //     (the counters themselves are being consumed by other threads of this launch).
+    for (int t = gt * 4; t < k.N2; t += gridDim.x * CS_THREADS * 4) {
+        int cs[5];
 #pragma unroll
-        for (int d = 1; d < 8; d <<= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xffffffffu, end, d);
-            end = o > end ? o : end;
+        for (int q = 0; q < 5; ++q) cs[q] = (t + q < k.N2) ? v.cellstart[coff + t + q] : kept_total;
+        if ((k.N2 & 3) == 0) {
+            *reinterpret_cast<float4*>(v.layer(sp.slot, L_OBSTACLES) + t) = make_float4(0.f, 0.f, 0.f, 0.f);  // map["points"].setConstant(0.0), :147
+            if (FULL) {
+                const int4 r = *reinterpret_cast<const int4*>(v.raw_i + coff + t);
+                *reinterpret_cast<float4*>(v.layer(sp.slot, L_RAW) + t) = make_float4((float)r.x, (float)r.y, (float)r.z, (float)r.w);
+                *reinterpret_cast<int4*>(v.raw_i + coff + t) = make_int4(0, 0, 0, 0);
+            }
         }
-        const unsigned long long line = begin + (unsigned long long)(lane & 7) * 128;  // up to 8 lines (1 KB) of each run
-        if (line < end) asm volatile("prefetch.global.L1 [%0];" ::"l"(line));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int cell = t + q;
+            if (cell >= k.N2) break;
+            if ((k.N2 & 3) != 0) {
+                v.layer(sp.slot, L_OBSTACLES)[cell] = 0.0f;
+                if (FULL) {
+                    v.layer(sp.slot, L_RAW)[cell] = (float)v.raw_i[coff + cell];
+                    v.raw_i[coff + cell] = 0;
+                }
+            }
+            if (cs[q + 1] == cs[q]) {
+                v.layer(sp.slot, L_COUNT)[cell] = 0.0f;
+                v.layer(sp.slot, L_VARIANCE)[cell] = 0.0f;
+                v.layer(sp.slot, L_MINH)[cell] = FLT_MAX;
+                if (FULL) {
+                    v.layer(sp.slot, L_M2)[cell] = 0.0f;
+                    v.layer(sp.slot, L_MEAN)[cell] = 0.0f;
+                    v.layer(sp.slot, L_GCAND)[cell] = 0.0f;
+                    v.layer(sp.slot, L_PLANEDIST)[cell] = 0.0f;
+                    v.layer(sp.slot, L_MAXH)[cell] = FLT_MIN;
+                }
+            }
+        }
     }
-    if (!live) return;
+    // (2) the worklist: non-empty cells grouped by count class (k_cell_place), so the 32 cells of a warp need (almost)
+    //     the same number of sequential steps; grid-stride (a warp's entries stay 32 consecutive ones)
+    const int wl_n = v.wl_count[2 * sp.slot];
+    const float oz = sp.oz;
+    for (int t = gt; t < wl_n; t += gridDim.x * CS_THREADS) {
+    const int cell = v.worklist[coff + t];
+    const unsigned long long cnt_runs = v.cnt64[coff + cell];
+    const int cnt = (int)(uint32_t)cnt_runs, runs = (int)(cnt_runs >> 32);
+    const int cstart = v.cellstart[coff + cell];
+    const float* zs = v.zsorted + (size_t)sp.slot * v.pcap + cstart;
+    uint2* dir = v.rundir + (size_t)sp.slot * v.pcap + cstart;
+    // the kernel is bound by the latency of dependent global loads: pull the first lines of the segment and of the
+    // run directory towards L1 right away
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(zs));
+    if (cnt > 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(zs + 32));
+    if (runs > 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(dir));
 
     float n = 0.0f, mean = 0.0f, m2 = 0.0f;
     float mn = FLT_MAX;
     float mx = FLT_MIN, gc = 0.0f, pdm = 0.0f;  // dead layers (FULL only)
-    // The recurrence is sequential, the loads are not: fetch up to 8 values at once so that a
-    // heavy cell pays one memory latency per 8 points instead of one per point.
-    for (int j0 = 0; j0 < cnt; j0 += 8) {
-        if (j0 + 64 < cnt) asm volatile("prefetch.global.L1 [%0];" ::"l"(zs + j0 + 64));  // long cells: stay two lines ahead
-        float zb[8];
+    // one accumulate step of insert_cloud (:282-309)
+    auto step = [&](float z) {
+        const float pd = __fsub_rn(z, oz);  // planeDist, :295
+        if (FULL) gc = (float)__ddiv_rn((double)__fadd_rn(z, __fmul_rn(n, gc)), __dadd_rn((double)n, 1.0));  // :296
+        if (mean == 0.0f) mean = pd;  // :298-299
+        if (!(pd != pd)) {            // :300
+            const float delta = __fsub_rn(pd, mean);
+            mean = __fadd_rn(mean, __fdiv_rn(delta, __fadd_rn(n, 1.0f)));
+            if (FULL) pdm = (float)__ddiv_rn((double)__fadd_rn(pd, __fmul_rn(n, pdm)), __dadd_rn((double)n, 1.0));
+            m2 = __fadd_rn(m2, __fmul_rn(delta, __fsub_rn(pd, mean)));
+        }
+        if (FULL) mx = (mx < z) ? z : mx;                   // std::max(maxHeight, z)
+        const float zl = __fsub_rn(z, 0.0001f);
+        mn = (zl < mn) ? zl : mn;                           // std::min(minHeight, z - 0.0001f)
+        n = __fadd_rn(n, 1.0f);
+    };
+
+    // The segment is a sequence of runs (k_rasterize), each internally in input order; input order of the cell = runs
+    // by ascending id.  The cell's directory (one entry per run, contiguous) is sorted by id first: up to 8 runs in
+    // registers (odd-even transposition), more -- cells crossed by many rings: walls, vehicles -- by an in-place Shell
+    // sort (gaps 57 / 23 / 10 / 4 / 1).
+    if (runs > 1 && runs <= 8) {
+        uint2 e[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) zb[q] = (j0 + q < cnt) ? zs[j0 + q] : 0.0f;
+        for (int q = 0; q < 8; ++q) e[q] = (q < runs) ? dir[q] : make_uint2(0xffffffffu, 0u);
+        bool moved = false;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            if (j0 + q >= cnt) break;
-            const float z = zb[q];
-            const float pd = __fsub_rn(z, oz);  // planeDist, :295
-            if (FULL) gc = (float)__ddiv_rn((double)__fadd_rn(z, __fmul_rn(n, gc)), __dadd_rn((double)n, 1.0));  // :296
-            if (mean == 0.0f) mean = pd;  // :298-299
-            if (!(pd != pd)) {            // :300
-                const float delta = __fsub_rn(pd, mean);
-                mean = __fadd_rn(mean, __fdiv_rn(delta, __fadd_rn(n, 1.0f)));
-                if (FULL) pdm = (float)__ddiv_rn((double)__fadd_rn(pd, __fmul_rn(n, pdm)), __dadd_rn((double)n, 1.0));
-                m2 = __fadd_rn(m2, __fmul_rn(delta, __fsub_rn(pd, mean)));
+        for (int pass = 0; pass < 8; ++pass) {
+#pragma unroll
+            for (int q = pass & 1; q + 1 < 8; q += 2) {
+                if (e[q + 1].x < e[q].x) {
+                    const uint2 tmp = e[q];
+                    e[q] = e[q + 1];
+                    e[q + 1] = tmp;
+                    moved = true;
+                }
             }
-            if (FULL) mx = (mx < z) ? z : mx;                   // std::max(maxHeight, z)
-            const float zl = __fsub_rn(z, 0.0001f);
-            mn = (zl < mn) ? zl : mn;                           // std::min(minHeight, z - 0.0001f)
-            n = __fadd_rn(n, 1.0f);
+        }
+        if (moved) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (q < runs) dir[q] = e[q];
+        }
+    } else if (runs > 8) {
+        const int gaps[5] = {57, 23, 10, 4, 1};
+#pragma unroll
+        for (int gi = 0; gi < 5; ++gi) {
+            const int gap = gaps[gi];
+            if (gap >= runs) continue;
+            for (int a = gap; a < runs; ++a) {
+                const uint2 e = dir[a];
+                int b = a;
+                while (b >= gap) {
+                    const uint2 f = dir[b - gap];
+                    if (f.x <= e.x) break;
+                    dir[b] = f;
+                    b -= gap;
+                }
+                if (b != a) dir[b] = e;
+            }
         }
     }
-    v.cnt_i[coff + cell] = 0;                      // consumed: zero again for the next scan
-    v.layer(sp.slot, L_OBSTACLES)[cell] = 0.0f;    // map["points"].setConstant(0.0), :147 (k_label counts into it)
+    // Streaming walk: chunks of up to 8 consecutive heights of the current run; the loads of the next chunk (and the
+    // directory entry of the next run) are in flight while the current chunk goes through the sequential recurrence.
+    {
+        int rj = 0, pb = 0, pe = cnt;   // runs == 1: the whole segment
+        if (runs > 1) {
+            const uint2 e0 = dir[0];
+            pb = (int)(e0.y & RUN_LOW26);
+            pe = pb + (int)(e0.y >> 26) + 1;
+        }
+        float zb[8], zn[8];
+        int mb = 0, mnx = 0;
+        auto fetch = [&](float* dst, int& m) {
+            m = min(8, pe - pb);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = (q < m) ? zs[pb + q] : 0.0f;
+            pb += m;
+            if (pb == pe && ++rj < runs) {
+                const uint2 en = dir[rj];
+                pb = (int)(en.y & RUN_LOW26);
+                pe = pb + (int)(en.y >> 26) + 1;
+                if (((pb + 8) & ~31) != (pb & ~31)) asm volatile("prefetch.global.L1 [%0];" ::"l"(zs + pb + 8));
+            }
+        };
+        fetch(zb, mb);
+        while (mb > 0) {
+            fetch(zn, mnx);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (q < mb) step(zb[q]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) zb[q] = zn[q];
+            mb = mnx;
+        }
+    }
+    v.cnt64[coff + cell] = 0ull;                   // consumed: zero again for the next scan
     v.layer(sp.slot, L_COUNT)[cell] = n;
     v.layer(sp.slot, L_VARIANCE)[cell] = __fdiv_rn(m2, __fadd_rn(n, FLT_MIN));
     v.layer(sp.slot, L_MINH)[cell] = mn;
@@ -525,8 +717,7 @@ __global__ void __launch_bounds__(128) k_cell_stats(View v, const SlotParams* __
         v.layer(sp.slot, L_GCAND)[cell] = gc;
         v.layer(sp.slot, L_PLANEDIST)[cell] = pdm;
         v.layer(sp.slot, L_MAXH)[cell] = mx;
-        v.layer(sp.slot, L_RAW)[cell] = (float)v.raw_i[coff + cell];
-        v.raw_i[coff + cell] = 0;
+    }
     }
 }
 
@@ -657,7 +848,7 @@ __device__ __forceinline__ bool detect_patch(const Const& k, const float (*sP)[D
 }
 
 template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(DT_X* DT_Y, MIN_BLOCKS) k_detect(View v, const SlotParams* __restrict__ batch) {
+__global__ void __launch_bounds__(DT_X* DT_Y, MIN_BLOCKS) k_detect_ldg(View v, const SlotParams* __restrict__ batch) {
     __shared__ float sP[DT_R][DT_W], sPV[DT_R][DT_W], sPM[DT_R][DT_W], sM[DT_R][DT_W];
     const SlotParams& sp = batch[blockIdx.z];
     const Const& k = v.k;
@@ -727,6 +918,246 @@ __global__ void __launch_bounds__(DT_X* DT_Y, MIN_BLOCKS) k_detect(View v, const
         // confidence of a cell only changes at its own visit(s), so decay(C) after patch
         // detection is exactly what the (first) visit will store; ring corners (i == j) are
         // visited twice and need the second decay as well.
+        const float d1 = decay_confidence(k, c);
+        float* D1 = v.roll_scratch + (size_t)sp.slot * 2 * k.N2;
+        D1[cell] = d1;
+        if (i == j) D1[k.N2 + cell] = decay_confidence(k, d1);
+    }
+}
+
+// ---- TMA-staged variant ------------------------------------------------------------------
+// The tile (+halo) of the three per-scan layers arrives by three cp.async.bulk.tensor loads (one elected thread, one
+// mbarrier); cells outside the map are zero-filled by the TMA unit, which is harmless because only cells [2, N-2)
+// compute and their windows stay inside the map (:325-337).  The innermost start coordinate of a TMA box must be
+// 16-byte aligned (measured on B200: a start at i0 - 2 raises "illegal instruction", tools/tma_probe4.cu), so the
+// tile keeps a halo of 4 cells in i: box = 40 x 12 x 1 at (i0 - 4, j0 - 2).  All layers of all slots form ONE 3-D tensor
+// (i, j, plane = slot * n_layers + layer), so one descriptor serves every scan.  While the tile is in flight the
+// threads fetch their own cell's G, C and table entry.
+//
+// Window sums.  The three block reductions of :359,374-375 are Eigen's binary-split tree over the column-major
+// coefficients e[k] = block(k % S, k / S).  Most inner nodes of that tree are runs of 2 or 3
+// consecutive rows of ONE column: pair(r, c) = q(r, c) + q(r+1, c) and triple(r, c) = q(r, c) + pair(r+1, c) -- the
+// very additions of the tree, so they can be computed once per tile position and shared by every window that contains
+// them (a 5x5 tree then needs 14 shared loads and 13 additions instead of 25 and 24).  The point-count sum is a sum of
+// small integers (exact in fp32 in any order) and the block minimum is order-free: both are separable (column
+// partials of 3 / 5 rows).  Tiles without a single candidate cell (psum >= need nowhere) skip the product stage.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+constexpr int DT_HX = 4;                 // halo in i of the TMA tile (alignment of the box start)
+constexpr int DT_WT = DT_X + 2 * DT_HX;  // 40
+
+struct __align__(128) DetectTile {
+    float P[DT_R][DT_WT];   // kept points per cell                       (TMA destination)
+    float V[DT_R][DT_WT];   // variance                                    (TMA destination)
+    float M[DT_R][DT_WT];   // min height                                  (TMA destination)
+    float C3[DT_R][DT_WT], C5[DT_R][DT_WT];       // sum of P over rows r .. r+2 / r .. r+4 of the column (exact integers)
+    float N3[DT_R][DT_WT], N5[DT_R][DT_WT];       // min of M over the same rows
+    float QV[DT_R][DT_WT], PV2[DT_R][DT_WT], TV[DT_R][DT_WT];   // q = P * V; pair; triple
+    float QM[DT_R][DT_WT], PM2[DT_R][DT_WT], TM[DT_R][DT_WT];   // q = P * M; pair; triple
+};
+static_assert(offsetof(DetectTile, V) % 128 == 0 && offsetof(DetectTile, M) % 128 == 0, "TMA destinations are 128-byte aligned");   // 12 * 40 * 4 = 1920 = 15 * 128
+
+// Eigen tree of a 5x5 / 3x3 window from the shared partials; (r0, c0) = window origin (row = i, col = j)
+__device__ __forceinline__ float tree25(const float (*Q)[DT_WT], const float (*P2)[DT_WT], const float (*T)[DT_WT], int r0, int c0) {
+#define QQ(r, c) Q[c0 + (c)][r0 + (r)]
+#define PP(r, c) P2[c0 + (c)][r0 + (r)]
+#define TT(r, c) T[c0 + (c)][r0 + (r)]
+    const float s0_6 = __fadd_rn(TT(0, 0), __fadd_rn(QQ(3, 0), __fadd_rn(QQ(4, 0), QQ(0, 1))));          // e0..e2 | e3 + (e4 + e5)
+    const float s6_6 = __fadd_rn(TT(1, 1), __fadd_rn(QQ(4, 1), PP(0, 2)));                                  // e6..e8 | e9 + (e10 + e11)
+    const float s12_6 = __fadd_rn(TT(2, 2), TT(0, 3));                                                      // e12..e14 | e15..e17
+    const float s18_7 = __fadd_rn(__fadd_rn(QQ(3, 3), __fadd_rn(QQ(4, 3), QQ(0, 4))), __fadd_rn(PP(1, 4), PP(3, 4)));  // e18 + (e19 + e20) | (e21 + e22) + (e23 + e24)
+    return __fadd_rn(__fadd_rn(s0_6, s6_6), __fadd_rn(s12_6, s18_7));
+#undef TT
+}
+__device__ __forceinline__ float tree9s(const float (*Q)[DT_WT], const float (*P2)[DT_WT], int r0, int c0) {
+    const float s0_4 = __fadd_rn(PP(0, 0), __fadd_rn(QQ(2, 0), QQ(0, 1)));                  // (e0 + e1) + (e2 + e3)
+    const float s4_5 = __fadd_rn(PP(1, 1), __fadd_rn(QQ(0, 2), PP(1, 2)));                  // (e4 + e5) + (e6 + (e7 + e8))
+    return __fadd_rn(s0_4, s4_5);
+#undef QQ
+#undef PP
+}
+
+// the decision part of detect_ground_patch<S> (:364-394) on the window quantities; returns true when (g, c) changed
+template <int S>
+__device__ __forceinline__ bool detect_decide(const Const& k, float psum, float localmin, float sumPV, float sumPM, float centerP, float variance, float vt,
+                                              float e, float& g, float& c) {
+    const float oc = c, og = g;
+    const float maxVar = (centerP >= k.pc_var_thresh_f) ? variance : __fdiv_rn(sumPV, psum);
+    const float groundlevel = __fdiv_rn(sumPM, psum);
+    const float gd = __fmul_rn(__fsub_rn(groundlevel, og), __fmul_rn(2.0f, oc));
+    const float groundDiff = (gd < 1.0f) ? 1.0f : gd;  // std::max(gd, 1.0f)
+    // do not update known high confidence estimations upward, :379
+    if ((double)oc > 0.5 && (double)groundlevel >= __dadd_rn((double)og, k.outlier_tol)) return false;
+    if ((double)vt > __dmul_rn((double)maxVar, (double)maxVar) && maxVar > 0.0f &&
+        (double)psum > __dmul_rn((double)__fmul_rn(__fmul_rn(groundDiff, e), (float)S), k.gp_thresh)) {
+        const double ncd = __ddiv_rn((double)psum, k.occ_factor);
+        const float nc = (float)((1.0 < ncd) ? 1.0 : ncd);  // std::min(ncd, 1.0)
+        const float num = __fadd_rn(__fmul_rn(groundlevel, nc), __fmul_rn(__fmul_rn(oc, og), 2.0f));
+        const float den = __fadd_rn(nc, __fmul_rn(oc, 2.0f));
+        g = __fdiv_rn(num, den);
+        const double cd = __ddiv_rn(__dadd_rn(__ddiv_rn((double)psum, k.occ_factor2), (double)oc), 2.0);
+        c = (float)((1.0 < cd) ? 1.0 : cd);
+        return true;
+    }
+    if (localmin < og) {
+        g = localmin;
+        const float t = __fadd_rn(oc, 0.1f);
+        c = (0.5f < t) ? 0.5f : t;  // std::min(oc + 0.1f, 0.5f)
+        return true;
+    }
+    return false;
+}
+
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(DT_X* DT_Y, MIN_BLOCKS) k_detect_tma(View v, const SlotParams* __restrict__ batch, const __grid_constant__ CUtensorMap tmap) {
+    __shared__ DetectTile s;
+    __shared__ __align__(8) uint64_t s_bar;
+    const SlotParams& sp = batch[blockIdx.z];
+    const Const& k = v.k;
+    const int N = k.N, N2 = k.N2;
+    const int i0 = blockIdx.x * DT_X, j0 = blockIdx.y * DT_Y;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * DT_X + tx;
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        constexpr uint32_t kBytes = 3u * DT_R * DT_WT * sizeof(float);
+        mbar_expect_tx(&s_bar, kBytes);
+        const int plane0 = sp.slot * v.n_layers;
+        tma_load_3d(&s.P[0][0], &tmap, &s_bar, i0 - DT_HX, j0 - DT_H, plane0 + L_COUNT);
+        tma_load_3d(&s.V[0][0], &tmap, &s_bar, i0 - DT_HX, j0 - DT_H, plane0 + L_VARIANCE);
+        tma_load_3d(&s.M[0][0], &tmap, &s_bar, i0 - DT_HX, j0 - DT_H, plane0 + L_MINH);
+    }
+    // own cell (overlaps the tile transfer)
+    float* const L0 = v.layer(sp.slot, 0);
+    const int i = i0 + tx, j = j0 + ty;
+    const bool live = i < N && j < N;
+    const int cell = i + j * N;
+    float g = 0.0f, c = 0.0f;
+    float4 tb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (live) {
+        g = L0[L_GROUND * N2 + cell];
+        c = L0[L_GROUNDPATCH * N2 + cell];
+        tb = __ldg(v.detect_tab + cell);
+    }
+    const int flags = __float_as_int(tb.w);
+    mbar_wait(&s_bar, 0);
+
+    // stage A: column partials of the point counts (exact) -- positions p = tid, tid + 256 of the 12 x 40 tile
+    for (int p = tid; p < DT_R * DT_WT; p += DT_X * DT_Y) {
+        const int row = p / DT_WT, col = p % DT_WT;   // row = j index of the tile, col = i index
+        float a[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) a[q] = (col + q < DT_WT) ? s.P[row][col + q] : 0.0f;
+        const float c3 = __fadd_rn(__fadd_rn(a[0], a[1]), a[2]);
+        s.C3[row][col] = c3;
+        s.C5[row][col] = __fadd_rn(__fadd_rn(c3, a[3]), a[4]);
+    }
+    __syncthreads();
+    const int li = tx + DT_HX, lj = ty + DT_H;
+    const bool inner = live && (flags & DTF_INNER);
+    const bool s5 = (flags & DTF_S5) != 0;
+    float psum = 0.0f;
+    if (inner) {
+        if (s5) {
+            const int r0 = li - 2, c0 = lj - 2;
+            psum = __fadd_rn(__fadd_rn(__fadd_rn(s.C5[c0][r0], s.C5[c0 + 1][r0]), __fadd_rn(s.C5[c0 + 2][r0], s.C5[c0 + 3][r0])), s.C5[c0 + 4][r0]);
+        } else {
+            const int r0 = li - 1, c0 = lj - 1;
+            psum = __fadd_rn(__fadd_rn(s.C3[c0][r0], s.C3[c0 + 1][r0]), s.C3[c0 + 2][r0]);
+        }
+    }
+    // early skipping of (almost) empty areas, :364 (both sides integer valued: the float compare is the double one)
+    const bool cand = inner && !(psum < tb.x);
+    const bool any = __syncthreads_or(cand);
+    bool changed = false;
+    if (any) {
+        // stage B: products, pairs, triples and column minima
+        for (int p = tid; p < DT_R * DT_WT; p += DT_X * DT_Y) {
+            const int row = p / DT_WT, col = p % DT_WT;
+            float qv[3], qm[3], m[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) m[q] = (col + q < DT_WT) ? s.M[row][col + q] : FLT_MAX;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const float pp = (col + q < DT_WT) ? s.P[row][col + q] : 0.0f;
+                const float vv = (col + q < DT_WT) ? s.V[row][col + q] : 0.0f;
+                qv[q] = __fmul_rn(pp, vv);
+                qm[q] = __fmul_rn(pp, m[q]);
+            }
+            s.QV[row][col] = qv[0];
+            s.QM[row][col] = qm[0];
+            const float pv12 = __fadd_rn(qv[1], qv[2]), pm12 = __fadd_rn(qm[1], qm[2]);
+            s.PV2[row][col] = __fadd_rn(qv[0], qv[1]);
+            s.PM2[row][col] = __fadd_rn(qm[0], qm[1]);
+            s.TV[row][col] = __fadd_rn(qv[0], pv12);
+            s.TM[row][col] = __fadd_rn(qm[0], pm12);
+            float n3 = m[0];
+            n3 = (m[1] < n3) ? m[1] : n3;
+            n3 = (m[2] < n3) ? m[2] : n3;
+            s.N3[row][col] = n3;
+            float n5 = (m[3] < n3) ? m[3] : n3;
+            n5 = (m[4] < n5) ? m[4] : n5;
+            s.N5[row][col] = n5;
+        }
+        __syncthreads();
+        if (cand) {
+            const float variance = s.V[lj][li], centerP = s.P[lj][li];
+            if (s5) {
+                const int r0 = li - 2, c0 = lj - 2;
+                float localmin = s.N5[c0][r0];
+#pragma unroll
+                for (int q = 1; q < 5; ++q) {
+                    const float t = s.N5[c0 + q][r0];
+                    localmin = (t < localmin) ? t : localmin;
+                }
+                changed = detect_decide<5>(k, psum, localmin, tree25(s.QV, s.PV2, s.TV, r0, c0), tree25(s.QM, s.PM2, s.TM, r0, c0), centerP, variance,
+                                           tb.y, tb.z, g, c);
+            } else {
+                const int r0 = li - 1, c0 = lj - 1;
+                float localmin = s.N3[c0][r0];
+#pragma unroll
+                for (int q = 1; q < 3; ++q) {
+                    const float t = s.N3[c0 + q][r0];
+                    localmin = (t < localmin) ? t : localmin;
+                }
+                changed = detect_decide<3>(k, psum, localmin, tree9s(s.QV, s.PV2, r0, c0), tree9s(s.QM, s.PM2, r0, c0), centerP, variance, tb.y, tb.z, g, c);
+            }
+        }
+    }
+    if (!live) return;
+    if (changed) {
+        L0[L_GROUND * N2 + cell] = g;
+        L0[L_GROUNDPATCH * N2 + cell] = c;
+    }
+    if (v.skew.sk) {
+        skew_store_cell(v, sp, cell, i, j, g, c, (flags & DTF_FAR) != 0);
+    } else if (v.spiral_recs) {
         const float d1 = decay_confidence(k, c);
         float* D1 = v.roll_scratch + (size_t)sp.slot * 2 * k.N2;
         D1[cell] = d1;
@@ -1226,7 +1657,7 @@ __global__ void __launch_bounds__(256) k_label(View v, const SlotParams* __restr
         const bool in = i < n;
         code[u] = in ? v.code[base + i] : (PC_ABSENT << 24);
         dist[u] = in ? v.dist[base + i] : 0.0f;
-        z[u] = in ? __uint_as_float(v.kz[base + i].y) : 0.0f;
+        z[u] = in ? __uint_as_float(v.zw[base + i].x) : 0.0f;
     }
 #pragma unroll
     for (int u = 0; u < LABEL_ILP; ++u) {
@@ -1379,6 +1810,55 @@ __global__ void __launch_bounds__(256) k_terrain_image(View v, int slot, float* 
     px[2] = raw[cell];
 }
 
+// f3, second half: the 8-bit image grid_map::GridMapCvConverter::toImage<unsigned char, 1>(map, layer, CV_8UC1, img)
+// hands to cv::applyColorMap (GroundGridNodelet.cpp:238-245): lower / upper = min / max over the finite cells of the
+// layer, pixel (i, j) = (unsigned char)(((value - lower) / (upper - lower)) * 255.f), non-finite cells stay 0.
+__device__ __forceinline__ bool finite_f(float x) { return fabsf(x) <= FLT_MAX; }
+
+__global__ void __launch_bounds__(256) k_layer_minmax(const float* __restrict__ layer, int n, float* __restrict__ mm) {
+    // mm[0] = min, mm[1] = max, as ordered-int atomics (initialised by the host to +inf / -inf patterns)
+    float lo = INFINITY, hi = -INFINITY;
+    for (int c = blockIdx.x * 256 + threadIdx.x; c < n; c += gridDim.x * 256) {
+        const float x = layer[c];
+        if (finite_f(x)) {
+            lo = fminf(lo, x);
+            hi = fmaxf(hi, x);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        // monotone float -> int mapping so that integer atomicMin / atomicMax order like the floats
+        auto key = [](float f) { const int b = __float_as_int(f); return b >= 0 ? b : (b ^ 0x7fffffff); };
+        atomicMin(reinterpret_cast<int*>(mm), key(lo));
+        atomicMax(reinterpret_cast<int*>(mm) + 1, key(hi));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_layer_image_u8(const float* __restrict__ layer, int N, const float* __restrict__ mm, unsigned char* __restrict__ dst) {
+    const int cell = blockIdx.x * 256 + threadIdx.x;
+    if (cell >= N * N) return;
+    auto unkey = [](int kx) { return __int_as_float(kx >= 0 ? kx : (kx ^ 0x7fffffff)); };
+    const float lower = unkey(reinterpret_cast<const int*>(mm)[0]), upper = unkey(reinterpret_cast<const int*>(mm)[1]);
+    const float x = layer[cell];
+    unsigned char px = 0;
+    if (finite_f(x)) {
+        const float t = __fmul_rn(__fdiv_rn(__fsub_rn(x, lower), __fsub_rn(upper, lower)), 255.0f);
+        px = (t == t) ? (unsigned char)(int)t : 0;   // (Type_) cast: truncation; a constant layer (0 / 0) has no defined image
+    }
+    const int i = cell % N, j = cell / N;
+    dst[(size_t)i * N + j] = px;   // cv::Mat row = index(0), col = index(1)
+}
+
+int launch_layer_image_u8(const View& v, const float* layer, float* mm, unsigned char* dst, cudaStream_t st) {
+    k_layer_minmax<<<148, 256, 0, st>>>(layer, v.k.N2, mm);
+    k_layer_image_u8<<<(v.k.N2 + 255) / 256, 256, 0, st>>>(layer, v.k.N, mm, dst);
+    return 2;
+}
+
 // f4: the tallies of scripts/eval_groundpoint_classifier.py:95-118 for one segmented cloud: per
 // ground-truth label id (carried in `ring`, scripts/kitti_data_publisher.py:122-132) the number of
 // points predicted non-ground (intensity 99) and ground (49).
@@ -1459,49 +1939,38 @@ int launch_roll(const View& v, const SlotParams* batch, int count, cudaStream_t 
 }
 
 int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int max_points, int stop_after, cudaStream_t st,
-                         Profiler* prof) {
+                         Profiler* prof, const CUtensorMap* layer_map) {
     int launches = 0;
-    const int pblocks = max(1, cdiv(max_points, 256));
-    const int nb = max(1, cdiv(max_points, SORT_TILE));
+    const int nb = max(1, cdiv(max_points, RASTER_TILE));
 
-    // radix sort, pass 1 (low digit): the tile histograms come out of k_rasterize itself
-    size_t sh = sizeof(int) << v.bits_lo;
     static const int raster_occ = getenv("GG_RASTER_OCC") ? atoi(getenv("GG_RASTER_OCC")) : 5;
     if (raster_occ >= 5)
-        GG_LAUNCH(K_RASTERIZE, k_rasterize<5><<<dim3(nb, count), SORT_THREADS, sh, st>>>(v, batch, nb));
+        GG_LAUNCH(K_RASTERIZE, k_rasterize<5><<<dim3(nb, count), RASTER_THREADS, 0, st>>>(v, batch));
     else
-        GG_LAUNCH(K_RASTERIZE, k_rasterize<4><<<dim3(nb, count), SORT_THREADS, sh, st>>>(v, batch, nb));
-    GG_LAUNCH(K_SCAN_LO_CELLS, k_scan_lo_cells<<<2 * count, 1024, 0, st>>>(v, batch, count, nb));
-    static const int scatter_occ = getenv("GG_SCATTER_OCC") ? atoi(getenv("GG_SCATTER_OCC")) : 5;
-    if (scatter_occ >= 5)
-        GG_LAUNCH(K_SORT_SCATTER1, (k_sort_scatter<false, 5><<<dim3(nb, count), SORT_THREADS, sh + ((size_t)(SORT_THREADS / 32) * 2 << v.bits_lo), st>>>(
-                                       v, batch, v.kz, v.kz2, nullptr, 0, v.bits_lo, nb)));
-    else
-        GG_LAUNCH(K_SORT_SCATTER1, (k_sort_scatter<false, 4><<<dim3(nb, count), SORT_THREADS, sh + ((size_t)(SORT_THREADS / 32) * 2 << v.bits_lo), st>>>(
-                                       v, batch, v.kz, v.kz2, nullptr, 0, v.bits_lo, nb)));
-    // pass 2 (high digit): its histogram was accumulated by the pass-1 scatter; (key2, z2) -> zsorted
-    sh = sizeof(int) << v.bits_hi;
-    GG_LAUNCH(K_SORT_SCAN2, k_sort_scan_hi<<<count, 1024, 0, st>>>(v, batch, nb));
-    if (scatter_occ >= 5)
-        GG_LAUNCH(K_SORT_SCATTER2, (k_sort_scatter<true, 5><<<dim3(nb, count), SORT_THREADS, sh + ((size_t)(SORT_THREADS / 32) * 2 << v.bits_hi), st>>>(
-                                       v, batch, v.kz2, nullptr, v.zsorted, v.bits_lo, v.bits_hi, nb)));
-    else
-        GG_LAUNCH(K_SORT_SCATTER2, (k_sort_scatter<true, 4><<<dim3(nb, count), SORT_THREADS, sh + ((size_t)(SORT_THREADS / 32) * 2 << v.bits_hi), st>>>(
-                                       v, batch, v.kz2, nullptr, v.zsorted, v.bits_lo, v.bits_hi, nb)));
-    launches += 5;
+        GG_LAUNCH(K_RASTERIZE, k_rasterize<4><<<dim3(nb, count), RASTER_THREADS, 0, st>>>(v, batch));
+    GG_LAUNCH(K_CELL_TILES, k_cell_tiles<<<dim3(v.cell_tiles, count), CT_THREADS, 0, st>>>(v, batch));
+    GG_LAUNCH(K_CELL_PLACE, k_cell_place<<<dim3(v.cell_tiles, count), CT_THREADS, 0, st>>>(v, batch));
+    GG_LAUNCH(K_SCATTER, k_scatter<<<dim3(max(1, cdiv(max_points, 256 * SCATTER_ILP)), count), 256, 0, st>>>(v, batch));
+    launches += 4;
 
     if (v.k.full_layers)
-        GG_LAUNCH(K_CELL_STATS, k_cell_stats<true><<<dim3(cdiv(cdiv(v.k.N, 8) * cdiv(v.k.N, 4), 4), count), 128, 0, st>>>(v, batch));
+        GG_LAUNCH(K_CELL_STATS, k_cell_stats<true><<<dim3(cdiv(v.k.N2, CS_THREADS * 4), count), CS_THREADS, 0, st>>>(v, batch));
     else
-        GG_LAUNCH(K_CELL_STATS, k_cell_stats<false><<<dim3(cdiv(cdiv(v.k.N, 8) * cdiv(v.k.N, 4), 4), count), 128, 0, st>>>(v, batch));
+        GG_LAUNCH(K_CELL_STATS, k_cell_stats<false><<<dim3(cdiv(v.k.N2, CS_THREADS * 4), count), CS_THREADS, 0, st>>>(v, batch));
     ++launches;
     if (stop_after == 1) return launches;
 
     static const int detect_occ = getenv("GG_DETECT_OCC") ? atoi(getenv("GG_DETECT_OCC")) : 5;
-    if (detect_occ >= 5)
-        GG_LAUNCH(K_DETECT, k_detect<5><<<dim3(cdiv(v.k.N, DT_X), cdiv(v.k.N, DT_Y), count), dim3(DT_X, DT_Y), 0, st>>>(v, batch));
+    const dim3 dgrid(cdiv(v.k.N, DT_X), cdiv(v.k.N, DT_Y), count);
+    if (layer_map) {   // TMA-staged tile (needs a 16-byte row pitch: N % 4 == 0)
+        if (detect_occ >= 5)
+            GG_LAUNCH(K_DETECT, k_detect_tma<5><<<dgrid, dim3(DT_X, DT_Y), 0, st>>>(v, batch, *layer_map));
+        else
+            GG_LAUNCH(K_DETECT, k_detect_tma<4><<<dgrid, dim3(DT_X, DT_Y), 0, st>>>(v, batch, *layer_map));
+    } else if (detect_occ >= 5)
+        GG_LAUNCH(K_DETECT, k_detect_ldg<5><<<dgrid, dim3(DT_X, DT_Y), 0, st>>>(v, batch));
     else
-        GG_LAUNCH(K_DETECT, k_detect<4><<<dim3(cdiv(v.k.N, DT_X), cdiv(v.k.N, DT_Y), count), dim3(DT_X, DT_Y), 0, st>>>(v, batch));
+        GG_LAUNCH(K_DETECT, k_detect_ldg<4><<<dgrid, dim3(DT_X, DT_Y), 0, st>>>(v, batch));
     ++launches;
     if (stop_after == 2) return launches;
 
@@ -1550,6 +2019,103 @@ int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int 
     GG_LAUNCH(K_LABEL, k_label<<<dim3(max(1, cdiv(max_points, 256 * LABEL_ILP)), count), 256, 0, st>>>(v, batch));
     ++launches;
     return launches;
+}
+
+// ------------------------------------------------------------------------------------------
+// Single phases / single cells on their own: the public per-phase methods of the reference class
+// (GroundSegmentation.h:56-62) -- detect_ground_patches, detect_ground_patch<S>, spiral_ground_interpolation,
+// interpolate_cell -- for callers that drive the phases themselves.  Same arithmetic as the pipeline kernels.
+// ------------------------------------------------------------------------------------------
+// GroundSegmentation::interpolate_cell (:445-465) for one cell, in place
+__global__ void k_interpolate_cell(View v, int slot, int x, int y) {
+    const Const& k = v.k;
+    const int N = k.N;
+    float* G = v.layer(slot, L_GROUND);
+    float* C = v.layer(slot, L_GROUNDPATCH);
+    float cc[9], pr[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        const int g = (x - 1 + q % 3) + (y - 1 + q / 3) * N;
+        cc[q] = C[g];
+        pr[q] = __fmul_rn(cc[q], G[g]);
+    }
+    const float h = G[x + y * N];
+    const float occ = cc[4];
+    const float s = __fadd_rn(tree9(cc), FLT_MIN);  // :457
+    const float avg = __fdiv_rn(tree9(pr), s);      // :458
+    G[x + y * N] = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, occ), avg), __fmul_rn(occ, h));  // :460
+    const float fc = (float)(N / 2 - 1);
+    const float fx = __fsub_rn((float)x, fc), fy = __fsub_rn((float)y, fc);
+    const double d2 = __dmul_rn(__dadd_rn(__dmul_rn((double)fx, (double)fx), __dmul_rn((double)fy, (double)fy)), k.res_sq);
+    if (d2 > 12.0) {  // :463
+        const double o = (double)occ;
+        const double dec = __dsub_rn(o, __ddiv_rn(o, k.dec_factor));
+        C[x + y * N] = (float)((dec < 0.001) ? 0.001 : dec);  // std::max(dec, 0.001)
+    }
+}
+
+// GroundSegmentation::detect_ground_patch<S> (:343-395) for one cell, reading the layers directly
+template <int S>
+__global__ void k_detect_cell(View v, int slot, int i, int j) {
+    const Const& k = v.k;
+    const int N = k.N, H = S / 2;
+    const float* P = v.layer(slot, L_COUNT);
+    const float* V = v.layer(slot, L_VARIANCE);
+    const float* M = v.layer(slot, L_MINH);
+    float* G = v.layer(slot, L_GROUND);
+    float* C = v.layer(slot, L_GROUNDPATCH);
+    const int cell = i + j * N;
+    auto at = [&](const float* L, int q) { return L[(i - H + q % S) + (j - H + q / S) * N]; };
+    const double di = __dsub_rn((double)i, (double)N / 2.0), dj = __dsub_rn((double)j, (double)N / 2.0);
+    const float sqdist = (float)__dmul_rn(__dadd_rn(__dmul_rn(di, di), __dmul_rn(dj, dj)), k.res_sq);  // :356
+    const float e = v.expected[cell];
+    const float psum = TreeSum<0, S * S>::run([&](int q) { return at(P, q); });
+    double need = floor(__dmul_rn(__dmul_rn(k.gp_thresh, (double)S), (double)e));
+    need = (need < 3.0) ? 3.0 : need;
+    if ((double)psum < need) return;  // :364
+    const double a = __dmul_rn((double)sqdist, k.df_sq);
+    const double m = (a < k.mdf_sq) ? k.mdf_sq : a;
+    const float vt = (float)((k.mdf10_sq < m) ? k.mdf10_sq : m);  // :369
+    float localmin = at(M, 0);
+    for (int q = 1; q < S * S; ++q) {
+        const float t = at(M, q);
+        localmin = (t < localmin) ? t : localmin;
+    }
+    const float sumPV = TreeSum<0, S * S>::run([&](int q) { return __fmul_rn(at(P, q), at(V, q)); });
+    const float sumPM = TreeSum<0, S * S>::run([&](int q) { return __fmul_rn(at(P, q), at(M, q)); });
+    float g = G[cell], c = C[cell];
+    if (detect_decide<S>(k, psum, localmin, sumPV, sumPM, P[cell], V[cell], vt, e, g, c)) {
+        G[cell] = g;
+        C[cell] = c;
+    }
+}
+
+int launch_detect_only(const View& v, const SlotParams* batch, int count, cudaStream_t st, Profiler* prof, const CUtensorMap* layer_map) {
+    const dim3 dgrid(cdiv(v.k.N, DT_X), cdiv(v.k.N, DT_Y), count);
+    if (layer_map)
+        GG_LAUNCH(K_DETECT, k_detect_tma<4><<<dgrid, dim3(DT_X, DT_Y), 0, st>>>(v, batch, *layer_map));
+    else
+        GG_LAUNCH(K_DETECT, k_detect_ldg<4><<<dgrid, dim3(DT_X, DT_Y), 0, st>>>(v, batch));
+    return 1;
+}
+
+// the plain level-scheduled wavefront on the normal layers (no skewed copy needed)
+int launch_spiral_only(const View& v, const SlotParams* batch, int count, cudaStream_t st, Profiler* prof) {
+    GG_LAUNCH(K_SPIRAL, k_spiral<<<count, SPIRAL_THREADS, 0, st>>>(v, batch));
+    return 1;
+}
+
+int launch_interpolate_cell(const View& v, int slot, int x, int y, cudaStream_t st) {
+    k_interpolate_cell<<<1, 1, 0, st>>>(v, slot, x, y);
+    return 1;
+}
+
+int launch_detect_cell(const View& v, int slot, int S, int i, int j, cudaStream_t st) {
+    if (S == 3)
+        k_detect_cell<3><<<1, 1, 0, st>>>(v, slot, i, j);
+    else
+        k_detect_cell<5><<<1, 1, 0, st>>>(v, slot, i, j);
+    return 1;
 }
 
 int launch_output(const View& v, const SlotParams* batch, int count, int max_points, bool want_cloud, cudaStream_t st,

@@ -1,9 +1,14 @@
 // groundgrid::GroundSegmentation -- same public surface as the reference class
 // (include/groundgrid/GroundSegmentation.h:48-62 there).  filter_cloud runs the whole per-scan
-// path on the GPU through gg_filter_cloud; the per-phase helper methods of the reference
-// (insert_cloud, detect_ground_patches, detect_ground_patch, spiral_ground_interpolation,
-// interpolate_cell) are thread entry points of its CPU implementation and have no stand-alone
-// meaning here: they are declared for source compatibility and throw std::logic_error.
+// path on the GPU through gg_filter_cloud.  The per-phase methods of the reference work too, at the
+// granularity the device path has:
+//   insert_cloud(cloud, 0, cloud->size(), ..)  resets the per-scan layers (what filter_cloud does at :61-75) and
+//       rasterises the WHOLE cloud; a sub-range [start, end) other than the whole cloud throws std::invalid_argument
+//       (the reference's ranges are its thread chunks accumulating into shared matrices; the device path has no
+//       partial-cloud accumulation).  The three index lists are filled like the reference's.
+//   detect_ground_patches(map, section)  section 0 runs the detection for the whole map, sections 1-3 are no-ops
+//       (the four sections are disjoint and order-free: their union is what one launch computes).
+//   detect_ground_patch<S>, spiral_ground_interpolation, interpolate_cell  as in the reference.
 #pragma once
 #include <sensor_msgs/PointCloud2.h>
 #include <geometry_msgs/TransformStamped.h>
@@ -40,10 +45,20 @@ class GroundSegmentation {
     /** Not in the reference: per-input-point labels (0 absent / 49 / 99) of the last filter_cloud call. */
     const std::vector<uint8_t>& lastLabels() const { return labels_; }
 
+    /** Not in the reference: filter_cloud fed with the raw sensor_msgs/PointCloud2 payload.  The unpack
+     *  (pcl::fromROSMsg, GroundGridNodelet.cpp:119-120) and the per-point transform into the map frame (:148-184;
+     *  T_map_from_frame = row-major 3x4 of lookupTransform("map", frame_id), null when the cloud is in "map" already)
+     *  run on the device (gg_upload_cloud_msg); returns the segmented cloud like filter_cloud. */
+    pcl::PointCloud<PCLPoint>::Ptr filter_cloud_msg(const sensor_msgs::PointCloud2& msg, const double* T_map_from_frame, const PCLPoint& cloudOrigin,
+                                                    const geometry_msgs::TransformStamped& mapToBase, grid_map::GridMap& map);
+
   protected:
     groundgrid::GroundGridConfig mConfig;
     size_t mDimension = 0;
     float mResolutionInit = 0.f;
     std::vector<uint8_t> labels_;
+
+  private:
+    void pushConfig(grid_map::GridMap& map) const;
 };
 }  // namespace groundgrid

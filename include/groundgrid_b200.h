@@ -121,7 +121,7 @@ int gg_init_map(gg_handle h, int slot, double x, double y, double z);
  * lookupTransform("base_link", "map").  *moved (may be NULL) = 1 if a cell shift happened. */
 int gg_update_pose(gg_handle h, int slot, double x, double y, const double T_base_from_map[12], int* moved);
 
-/* Batched gg_update_pose: `count` distinct slots, xy = 2 doubles per slot, T = 12 doubles per
+/* Batched gg_update_pose: `count` distinct slots (a repeated slot is GG_E_ARG), xy = 2 doubles per slot, T = 12 doubles per
  * slot, moved (may be NULL) = 1 int per slot.  One roll launch covers all slots. */
 int gg_update_pose_batch(gg_handle h, int count, const int* slots, const double* xy, const double* T, int* moved);
 
@@ -177,6 +177,24 @@ int gg_run_scans(gg_handle h, int count, const gg_scan_desc* scans, int stop_aft
 int gg_download_labels(gg_handle h, int slot, uint8_t* labels_out, size_t n);
 int gg_synchronize(gg_handle h);
 
+/* The per-phase methods of the reference class, for callers that drive the phases themselves
+ * (include/groundgrid/GroundSegmentation.h:56-62; all enqueue on the slot's stream):
+ *   gg_run_scans(.., stop_after = 1)  = the layer reset of filter_cloud (:61-75) + insert_cloud over the whole cloud
+ *                                       (:200-311); gg_get_point_classes then returns, per input point,
+ *                                       class << 24 | cell with class 0 absent, 1 kept, 2 kept (border cell),
+ *                                       3 ignored, 4 ignored (border cell), 5 outlier -- the contents of the
+ *                                       point_index / ignored / outliers lists of :112-117
+ *   gg_detect_ground_patches          = detect_ground_patches for all four sections (:314-340; sections are disjoint
+ *                                       and every cell only writes itself, so their union is order-free)
+ *   gg_detect_ground_patch            = detect_ground_patch<patch_size>(map, i, j) for one cell (:343-395)
+ *   gg_spiral_ground_interpolation    = spiral_ground_interpolation (:398-441), base_z = z of toBase * (0,0,0)
+ *   gg_interpolate_cell               = interpolate_cell(map, x, y) (:445-465)                                   */
+int gg_get_point_classes(gg_handle h, int slot, uint32_t* codes, size_t n);
+int gg_detect_ground_patches(gg_handle h, int slot);
+int gg_detect_ground_patch(gg_handle h, int slot, int patch_size, int i, int j);
+int gg_spiral_ground_interpolation(gg_handle h, int slot, double base_z);
+int gg_interpolate_cell(gg_handle h, int slot, int x, int y);
+
 /* Like gg_run_scans, but scan k reads its cloud from the caller-owned DEVICE buffer dev_points[k]
  * (n_points 32-byte records, 16-byte aligned) instead of the slot's upload buffer.  The buffer
  * must stay valid until the work is complete (and until gg_get_output, if that is used). */
@@ -200,6 +218,12 @@ int gg_run_scans_device(gg_handle h, int count, const gg_scan_desc* scans, const
 int gg_upload_cloud_msg(gg_handle h, int slot, const void* data, size_t n_points, int point_step, const int field_offsets[5],
                         const double T_map_from_frame[12]);
 int gg_terrain_image(gg_handle h, int slot, float* dst);
+/* The other branch of publish_grid_map_layer (src/GroundGridNodelet.cpp:238-245): the single-channel 8-bit image that
+ * grid_map::GridMapCvConverter::toImage<unsigned char, 1>(map, layer, CV_8UC1, img) produces and cv::applyColorMap then
+ * colours -- lower / upper = min / max over the finite cells, pixel (i, j) = (uchar)((v - lower) / (upper - lower) * 255),
+ * non-finite cells 0.  dst: N*N bytes, row-major (i, j) like the cv::Mat; lower / upper (may be NULL) receive the range.
+ * The colour table itself (cv::COLORMAP_TWILIGHT, 256 BGR triples) is OpenCV data: the caller applies it. */
+int gg_layer_image_u8(gg_handle h, int slot, const char* name, uint8_t* dst, float* lower, float* upper);
 int gg_eval_accumulate(gg_handle h, int slot);
 int gg_eval_read(gg_handle h, uint64_t* counts, int reset);
 

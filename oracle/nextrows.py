@@ -53,3 +53,18 @@ def eval_counts(labels, rings, n_ids=1024):
     ok = r < n_ids
     np.add.at(counts, (r[ok], ng[ok]), 1)
     return counts
+
+
+def layer_image_u8(layer):
+    """grid_map::GridMapCvConverter::toImage<unsigned char, 1>(map, layer, CV_8UC1, img) as called by
+    publish_grid_map_layer (src/GroundGridNodelet.cpp:238-245; grid_map_cv 1.6.x GridMapCvConverter.hpp): range = min / max
+    over the finite cells, pixel = (uchar)(((v - lower) / (upper - lower)) * 255.f) in fp32, non-finite cells 0."""
+    a = np.asarray(layer, np.float32)
+    fin = np.isfinite(a)
+    lower, upper = np.float32(a[fin].min()), np.float32(a[fin].max())
+    with np.errstate(invalid="ignore", divide="ignore"):
+        t = ((a - lower) / (upper - lower)) * np.float32(255.0)
+    img = np.zeros(a.shape, np.uint8)
+    ok = fin & np.isfinite(t)
+    img[ok] = t[ok].astype(np.int32).astype(np.uint8)
+    return img, float(lower), float(upper)

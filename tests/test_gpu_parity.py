@@ -561,3 +561,39 @@ def test_error_codes():
     with pytest.raises(capi.GroundGridError) as e:
         g.init_map(0, 0, 0, slot=7)
     assert e.value.code == -1
+
+
+@pytest.mark.parametrize("cfg", ["cfg2_300", "cfg3_600", "cfg4_364"])
+def test_cuda_path_against_the_reference_itself(cfg):
+    """The CUDA path against oracle/_ref (the UNMODIFIED reference sources on CPU stand-ins, prebuilt in the container
+    that has /root/reference) at BASELINE.json's full sizes: three scans with a map roll, labels / output order / every
+    layer bit for bit."""
+    from oracle import ref as refmod
+
+    if not refmod.available():
+        pytest.skip("oracle/_ref/libgg_ref.so was not shipped")
+    dim, res, scan, maxp = {"cfg2_300": (99.0, 0.33, synth.scan_64, 140000), "cfg3_600": (120.0, 0.2, synth.scan_128, 280000),
+                            "cfg4_364": (120.0, 0.33, synth.scan_4lidar, 520000)}[cfg]
+    g = capi.GroundGridB200(dim, res, n_slots=1, max_points=maxp, full_layers=True)
+    r = refmod.Reference(dim, res)
+    assert g.n == r.n
+    assert np.array_equal(g.layer("expectedPoints"), r.expected_points())
+    g.init_map(0.0, 0.0, 0.0)
+    r.init_map(0.0, 0.0, 0.0)
+    scene = synth.make_scene(seed=4321, stream_len=20.0, undulation=0.3)
+    rng = np.random.default_rng(17)
+    for k in range(3):
+        ex, ey, yaw = 1.1 * k, -0.45 * k, 0.01 * k
+        pts, org = scan(scene, (ex, ey), yaw, seed=700 + k)
+        if k:
+            q, t = refmod.base_from_map_qt(ex, ey, yaw, 0.0, pitch=0.02)
+            assert g.update_pose(ex, ey, refmod.tf2_matrix(q, t)) == bool(r.update(ex, ey, q, t))
+            assert np.array_equal(g.position(), r.position())
+            idx = rng.choice(len(pts), 2000, replace=False)
+            pts["z"][idx] -= rng.uniform(0.25, 2.0, 2000).astype(np.float32)
+        labels, index, _ = g.filter_cloud(pts, org, 0.0, want_index=True)
+        lab_r, idx_r, _ = r.filter_cloud(pts, org, 0.0)
+        assert np.array_equal(labels, lab_r), f"{cfg} scan {k}: {(labels != lab_r).sum()} labels differ from the reference"
+        assert np.array_equal(index, idx_r)
+        assert_layers_equal(g, r, ("points",) + LIVE + DEAD, f"{cfg} scan {k} vs reference")
+    g.close()
