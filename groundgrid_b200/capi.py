@@ -186,6 +186,7 @@ class GroundGridB200:
         _check(self._l.gg_create(float(dimension_m), np.float32(resolution), int(device), int(n_slots), int(max_points),
                                  flags, C.c_void_p(stream) if stream else None, C.byref(h)))
         self._h = h
+        self.device = int(device)
         self.n = self._l.gg_cells_per_side(h)
         self.n_slots = n_slots
         self.max_points = max_points

@@ -340,7 +340,8 @@ struct gg_handle_s {
     bool inputs_busy = false;  // asynchronous work that reads or writes the slots' input buffers may be in flight
     std::vector<cudaEvent_t> batch_ev;                    // unit hand-over events of gg_filter_cloud_batch
     cudaEvent_t raw_ev[8] = {};      // throttle of the raw copies issued by the mixing loop
-    int raw_gate = 2;                // GG_RAW_GATE: no raw copies while this many packed clouds wait for the bus
+    int raw_gate = 2;                // GG_RAW_GATE (legacy, only with GG_BUS_TARGET_MB=0): no raw copies while this many packed clouds wait for the bus
+    size_t bus_target = 8u << 20;    // GG_BUS_TARGET_MB: raw clouds are added while fewer bytes than this are in flight on the bus
     int raw_depth = 4;               // GG_RAW_DEPTH: raw copies in flight before the loop stops claiming more
     size_t last_raw = 0, last_packed = 0;  // scans sent raw / packed by the last batch call
     size_t last_raw_bytes = 0, last_packed_bytes = 0;
@@ -822,6 +823,7 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
     if (const char* e = getenv("GG_COPY_STREAMS")) h->n_copy_in = std::min(8, std::max(1, atoi(e)));
     if (const char* e = getenv("GG_MAIN_HELP")) h->main_help = atoi(e);
     if (const char* e = getenv("GG_RAW_GATE")) h->raw_gate = std::max(1, atoi(e));
+    if (const char* e = getenv("GG_BUS_TARGET_MB")) h->bus_target = (size_t)std::max(0, atoi(e)) << 20;
     if (const char* e = getenv("GG_RAW_DEPTH")) h->raw_depth = std::min(8, std::max(1, atoi(e)));
     if (const char* e = getenv("GG_HOST_PACK")) {
         h->host_pack = atoi(e) ? 1 : 0;
@@ -1512,7 +1514,8 @@ int gg_filter_cloud_batch_begin(gg_handle h, int count, const gg_scan_desc* scan
                 if (armed) p->cancel();
             }
         } pack_guard{h->packer};
-        int front = 0, back = count, raw_issued = 0, n_copies = 0;
+        int front = 0, back = count, raw_issued = 0, raw_done = 0, n_copies = 0;
+        size_t last_packed_bytes = 14 * (size_t)h->pcap, last_raw_bytes = sizeof(gg_point) * (size_t)h->pcap;   // size of the latest copy of either kind
         while (front < back) {
             poll_copies();
             if (h->packer->packed(jobs[front])) {
@@ -1526,15 +1529,22 @@ int gg_filter_cloud_batch_begin(gg_handle h, int count, const gg_scan_desc* scan
                 sent_packed[front] = 1;
                 ++h->last_packed;
                 h->last_packed_bytes += 14 * n_pad;
+                last_packed_bytes = 14 * n_pad;
                 if ((rc = delivered(front))) return rc;
                 ++front;
                 continue;
             }
-            // A raw cloud costs 32 B/point of bus time, a packed one 14: raw copies are only worth it while the
-            // packed clouds do not queue up themselves (then the bus, not the packers, is what limits the batch).
-            const bool packed_backlog = h->pack_issued - h->packer->copied.load(std::memory_order_relaxed) >= (uint64_t)h->raw_gate;
-            const bool bus_free = h->host_pack_mix && !packed_backlog &&
-                                  (raw_issued < h->raw_depth || cudaEventQuery(h->raw_ev[raw_issued % h->raw_depth]) == cudaSuccess);
+            // A raw cloud costs 32 B/point of bus time, a packed one 14, so packed clouds go first whenever one is ready.
+            // What the packers cannot fill is topped up with raw clouds: the measure is the number of BYTES in flight on
+            // the bus (copies issued and not yet completed, both kinds).  Below the target the DMA engines would run dry
+            // before the next packed cloud arrives, so a raw one is added; above it the bus is the limit and a raw cloud
+            // would only delay cheaper packed ones.  The split therefore follows the measured rates of the packers and of
+            // the bus on this host (CPU quota, ranks sharing the socket) instead of a fixed gate.
+            while (raw_done < raw_issued && cudaEventQuery(h->raw_ev[raw_done % h->raw_depth]) == cudaSuccess) ++raw_done;
+            const uint64_t packed_in_flight = h->pack_issued - h->packer->copied.load(std::memory_order_relaxed);
+            const size_t in_flight_bytes = (size_t)packed_in_flight * last_packed_bytes + (size_t)(raw_issued - raw_done) * last_raw_bytes;
+            const bool below_target = h->bus_target ? in_flight_bytes < h->bus_target : packed_in_flight < (uint64_t)h->raw_gate;
+            const bool bus_free = h->host_pack_mix && below_target && (raw_issued - raw_done) < h->raw_depth;
             int j = bus_free ? h->packer->claim_raw_from_back() : -1;
             if (j >= 0) {
                 const gg_scan_desc& d = scans[order[j]];
@@ -1545,6 +1555,7 @@ int gg_filter_cloud_batch_begin(gg_handle h, int count, const gg_scan_desc* scan
                 ++raw_issued;
                 ++h->last_raw;
                 h->last_raw_bytes += d.n_points * sizeof(gg_point);
+                last_raw_bytes = d.n_points * sizeof(gg_point);
                 back = j;
                 if ((rc = delivered(j))) return rc;
                 continue;

@@ -972,16 +972,19 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 constexpr int DT_HX = 4;                 // halo in i of the TMA tile (alignment of the box start)
 constexpr int DT_WT = DT_X + 2 * DT_HX;  // 40
 
+struct __align__(128) DetectRaw {   // one pipeline stage: the three TMA destinations
+    float P[DT_R][DT_WT];   // kept points per cell
+    float V[DT_R][DT_WT];   // variance
+    float M[DT_R][DT_WT];   // min height
+};
 struct __align__(128) DetectTile {
-    float P[DT_R][DT_WT];   // kept points per cell                       (TMA destination)
-    float V[DT_R][DT_WT];   // variance                                    (TMA destination)
-    float M[DT_R][DT_WT];   // min height                                  (TMA destination)
+    DetectRaw raw[2];       // double buffer: the tile after next is in flight while this one is computed
     float C3[DT_R][DT_WT], C5[DT_R][DT_WT];       // sum of P over rows r .. r+2 / r .. r+4 of the column (exact integers)
     float N3[DT_R][DT_WT], N5[DT_R][DT_WT];       // min of M over the same rows
     float QV[DT_R][DT_WT], PV2[DT_R][DT_WT], TV[DT_R][DT_WT];   // q = P * V; pair; triple
     float QM[DT_R][DT_WT], PM2[DT_R][DT_WT], TM[DT_R][DT_WT];   // q = P * M; pair; triple
 };
-static_assert(offsetof(DetectTile, V) % 128 == 0 && offsetof(DetectTile, M) % 128 == 0, "TMA destinations are 128-byte aligned");   // 12 * 40 * 4 = 1920 = 15 * 128
+static_assert(offsetof(DetectRaw, V) % 128 == 0 && offsetof(DetectRaw, M) % 128 == 0 && sizeof(DetectRaw) % 128 == 0, "TMA destinations are 128-byte aligned");   // 12 * 40 * 4 = 1920 = 15 * 128
 
 // Eigen tree of a 5x5 / 3x3 window from the shared partials; (r0, c0) = window origin (row = i, col = j)
 __device__ __forceinline__ float tree25(const float (*Q)[DT_WT], const float (*P2)[DT_WT], const float (*T)[DT_WT], int r0, int c0) {
@@ -1034,134 +1037,155 @@ __device__ __forceinline__ bool detect_decide(const Const& k, float psum, float 
     return false;
 }
 
+// A CTA walks DT_TILES consecutive tiles along j; the TMA loads of tile k + 1 are issued before tile k is computed
+// (two stages of raw tiles, one mbarrier each, phase parity flips every second use).
+constexpr int DT_TILES = 4;
+
 template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(DT_X* DT_Y, MIN_BLOCKS) k_detect_tma(View v, const SlotParams* __restrict__ batch, const __grid_constant__ CUtensorMap tmap) {
     __shared__ DetectTile s;
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_bar[2];
     const SlotParams& sp = batch[blockIdx.z];
     const Const& k = v.k;
     const int N = k.N, N2 = k.N2;
-    const int i0 = blockIdx.x * DT_X, j0 = blockIdx.y * DT_Y;
+    const int i0 = blockIdx.x * DT_X;
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * DT_X + tx;
-    if (tid == 0) mbar_init(&s_bar, 1);
-    __syncthreads();
-    if (tid == 0) {
+    const int tile0 = blockIdx.y * DT_TILES;
+    const int n_tiles = min(DT_TILES, (N + DT_Y - 1) / DT_Y - tile0);
+    const int plane0 = sp.slot * v.n_layers;
+    auto issue = [&](int kk) {   // one thread: loads of tile kk into stage kk & 1
         constexpr uint32_t kBytes = 3u * DT_R * DT_WT * sizeof(float);
-        mbar_expect_tx(&s_bar, kBytes);
-        const int plane0 = sp.slot * v.n_layers;
-        tma_load_3d(&s.P[0][0], &tmap, &s_bar, i0 - DT_HX, j0 - DT_H, plane0 + L_COUNT);
-        tma_load_3d(&s.V[0][0], &tmap, &s_bar, i0 - DT_HX, j0 - DT_H, plane0 + L_VARIANCE);
-        tma_load_3d(&s.M[0][0], &tmap, &s_bar, i0 - DT_HX, j0 - DT_H, plane0 + L_MINH);
-    }
-    // own cell (overlaps the tile transfer)
-    float* const L0 = v.layer(sp.slot, 0);
-    const int i = i0 + tx, j = j0 + ty;
-    const bool live = i < N && j < N;
-    const int cell = i + j * N;
-    float g = 0.0f, c = 0.0f;
-    float4 tb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    if (live) {
-        g = L0[L_GROUND * N2 + cell];
-        c = L0[L_GROUNDPATCH * N2 + cell];
-        tb = __ldg(v.detect_tab + cell);
-    }
-    const int flags = __float_as_int(tb.w);
-    mbar_wait(&s_bar, 0);
-
-    // stage A: column partials of the point counts (exact) -- positions p = tid, tid + 256 of the 12 x 40 tile
-    for (int p = tid; p < DT_R * DT_WT; p += DT_X * DT_Y) {
-        const int row = p / DT_WT, col = p % DT_WT;   // row = j index of the tile, col = i index
-        float a[5];
-#pragma unroll
-        for (int q = 0; q < 5; ++q) a[q] = (col + q < DT_WT) ? s.P[row][col + q] : 0.0f;
-        const float c3 = __fadd_rn(__fadd_rn(a[0], a[1]), a[2]);
-        s.C3[row][col] = c3;
-        s.C5[row][col] = __fadd_rn(__fadd_rn(c3, a[3]), a[4]);
+        DetectRaw& r = s.raw[kk & 1];
+        uint64_t* bar = &s_bar[kk & 1];
+        const int j0 = (tile0 + kk) * DT_Y;
+        mbar_expect_tx(bar, kBytes);
+        tma_load_3d(&r.P[0][0], &tmap, bar, i0 - DT_HX, j0 - DT_H, plane0 + L_COUNT);
+        tma_load_3d(&r.V[0][0], &tmap, bar, i0 - DT_HX, j0 - DT_H, plane0 + L_VARIANCE);
+        tma_load_3d(&r.M[0][0], &tmap, bar, i0 - DT_HX, j0 - DT_H, plane0 + L_MINH);
+    };
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
     }
     __syncthreads();
+    if (tid == 0) issue(0);
+    float* const L0 = v.layer(sp.slot, 0);
+    const int i = i0 + tx;
     const int li = tx + DT_HX, lj = ty + DT_H;
-    const bool inner = live && (flags & DTF_INNER);
-    const bool s5 = (flags & DTF_S5) != 0;
-    float psum = 0.0f;
-    if (inner) {
-        if (s5) {
-            const int r0 = li - 2, c0 = lj - 2;
-            psum = __fadd_rn(__fadd_rn(__fadd_rn(s.C5[c0][r0], s.C5[c0 + 1][r0]), __fadd_rn(s.C5[c0 + 2][r0], s.C5[c0 + 3][r0])), s.C5[c0 + 4][r0]);
-        } else {
-            const int r0 = li - 1, c0 = lj - 1;
-            psum = __fadd_rn(__fadd_rn(s.C3[c0][r0], s.C3[c0 + 1][r0]), s.C3[c0 + 2][r0]);
+    for (int kk = 0; kk < n_tiles; ++kk) {
+        // every thread is past the previous tile (barrier at the end of the loop body): its stage may be refilled
+        if (tid == 0 && kk + 1 < n_tiles) issue(kk + 1);
+        const DetectRaw& raw = s.raw[kk & 1];
+        // own cell (overlaps the tile transfer)
+        const int j = (tile0 + kk) * DT_Y + ty;
+        const bool live = i < N && j < N;
+        const int cell = i + j * N;
+        float g = 0.0f, c = 0.0f;
+        float4 tb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (live) {
+            g = L0[L_GROUND * N2 + cell];
+            c = L0[L_GROUNDPATCH * N2 + cell];
+            tb = __ldg(v.detect_tab + cell);
         }
-    }
-    // early skipping of (almost) empty areas, :364 (both sides integer valued: the float compare is the double one)
-    const bool cand = inner && !(psum < tb.x);
-    const bool any = __syncthreads_or(cand);
-    bool changed = false;
-    if (any) {
-        // stage B: products, pairs, triples and column minima
+        const int flags = __float_as_int(tb.w);
+        mbar_wait(&s_bar[kk & 1], (uint32_t)((kk >> 1) & 1));
+
+        // stage A: column partials of the point counts (exact) -- positions p = tid, tid + 256 of the 12 x 40 tile
         for (int p = tid; p < DT_R * DT_WT; p += DT_X * DT_Y) {
-            const int row = p / DT_WT, col = p % DT_WT;
-            float qv[3], qm[3], m[5];
+            const int row = p / DT_WT, col = p % DT_WT;   // row = j index of the tile, col = i index
+            float a[5];
 #pragma unroll
-            for (int q = 0; q < 5; ++q) m[q] = (col + q < DT_WT) ? s.M[row][col + q] : FLT_MAX;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const float pp = (col + q < DT_WT) ? s.P[row][col + q] : 0.0f;
-                const float vv = (col + q < DT_WT) ? s.V[row][col + q] : 0.0f;
-                qv[q] = __fmul_rn(pp, vv);
-                qm[q] = __fmul_rn(pp, m[q]);
-            }
-            s.QV[row][col] = qv[0];
-            s.QM[row][col] = qm[0];
-            const float pv12 = __fadd_rn(qv[1], qv[2]), pm12 = __fadd_rn(qm[1], qm[2]);
-            s.PV2[row][col] = __fadd_rn(qv[0], qv[1]);
-            s.PM2[row][col] = __fadd_rn(qm[0], qm[1]);
-            s.TV[row][col] = __fadd_rn(qv[0], pv12);
-            s.TM[row][col] = __fadd_rn(qm[0], pm12);
-            float n3 = m[0];
-            n3 = (m[1] < n3) ? m[1] : n3;
-            n3 = (m[2] < n3) ? m[2] : n3;
-            s.N3[row][col] = n3;
-            float n5 = (m[3] < n3) ? m[3] : n3;
-            n5 = (m[4] < n5) ? m[4] : n5;
-            s.N5[row][col] = n5;
+            for (int q = 0; q < 5; ++q) a[q] = (col + q < DT_WT) ? raw.P[row][col + q] : 0.0f;
+            const float c3 = __fadd_rn(__fadd_rn(a[0], a[1]), a[2]);
+            s.C3[row][col] = c3;
+            s.C5[row][col] = __fadd_rn(__fadd_rn(c3, a[3]), a[4]);
         }
         __syncthreads();
-        if (cand) {
-            const float variance = s.V[lj][li], centerP = s.P[lj][li];
+        const bool inner = live && (flags & DTF_INNER);
+        const bool s5 = (flags & DTF_S5) != 0;
+        float psum = 0.0f;
+        if (inner) {
             if (s5) {
                 const int r0 = li - 2, c0 = lj - 2;
-                float localmin = s.N5[c0][r0];
-#pragma unroll
-                for (int q = 1; q < 5; ++q) {
-                    const float t = s.N5[c0 + q][r0];
-                    localmin = (t < localmin) ? t : localmin;
-                }
-                changed = detect_decide<5>(k, psum, localmin, tree25(s.QV, s.PV2, s.TV, r0, c0), tree25(s.QM, s.PM2, s.TM, r0, c0), centerP, variance,
-                                           tb.y, tb.z, g, c);
+                psum = __fadd_rn(__fadd_rn(__fadd_rn(s.C5[c0][r0], s.C5[c0 + 1][r0]), __fadd_rn(s.C5[c0 + 2][r0], s.C5[c0 + 3][r0])), s.C5[c0 + 4][r0]);
             } else {
                 const int r0 = li - 1, c0 = lj - 1;
-                float localmin = s.N3[c0][r0];
-#pragma unroll
-                for (int q = 1; q < 3; ++q) {
-                    const float t = s.N3[c0 + q][r0];
-                    localmin = (t < localmin) ? t : localmin;
-                }
-                changed = detect_decide<3>(k, psum, localmin, tree9s(s.QV, s.PV2, r0, c0), tree9s(s.QM, s.PM2, r0, c0), centerP, variance, tb.y, tb.z, g, c);
+                psum = __fadd_rn(__fadd_rn(s.C3[c0][r0], s.C3[c0 + 1][r0]), s.C3[c0 + 2][r0]);
             }
         }
-    }
-    if (!live) return;
-    if (changed) {
-        L0[L_GROUND * N2 + cell] = g;
-        L0[L_GROUNDPATCH * N2 + cell] = c;
-    }
-    if (v.skew.sk) {
-        skew_store_cell(v, sp, cell, i, j, g, c, (flags & DTF_FAR) != 0);
-    } else if (v.spiral_recs) {
-        const float d1 = decay_confidence(k, c);
-        float* D1 = v.roll_scratch + (size_t)sp.slot * 2 * k.N2;
-        D1[cell] = d1;
-        if (i == j) D1[k.N2 + cell] = decay_confidence(k, d1);
+        // early skipping of (almost) empty areas, :364 (both sides integer valued: the float compare is the double one)
+        const bool cand = inner && !(psum < tb.x);
+        const bool any = __syncthreads_or(cand);
+        bool changed = false;
+        if (any) {
+            // stage B: products, pairs, triples and column minima
+            for (int p = tid; p < DT_R * DT_WT; p += DT_X * DT_Y) {
+                const int row = p / DT_WT, col = p % DT_WT;
+                float qv[3], qm[3], m[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) m[q] = (col + q < DT_WT) ? raw.M[row][col + q] : FLT_MAX;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const float pp = (col + q < DT_WT) ? raw.P[row][col + q] : 0.0f;
+                    const float vv = (col + q < DT_WT) ? raw.V[row][col + q] : 0.0f;
+                    qv[q] = __fmul_rn(pp, vv);
+                    qm[q] = __fmul_rn(pp, m[q]);
+                }
+                s.QV[row][col] = qv[0];
+                s.QM[row][col] = qm[0];
+                const float pv12 = __fadd_rn(qv[1], qv[2]), pm12 = __fadd_rn(qm[1], qm[2]);
+                s.PV2[row][col] = __fadd_rn(qv[0], qv[1]);
+                s.PM2[row][col] = __fadd_rn(qm[0], qm[1]);
+                s.TV[row][col] = __fadd_rn(qv[0], pv12);
+                s.TM[row][col] = __fadd_rn(qm[0], pm12);
+                float n3 = m[0];
+                n3 = (m[1] < n3) ? m[1] : n3;
+                n3 = (m[2] < n3) ? m[2] : n3;
+                s.N3[row][col] = n3;
+                float n5 = (m[3] < n3) ? m[3] : n3;
+                n5 = (m[4] < n5) ? m[4] : n5;
+                s.N5[row][col] = n5;
+            }
+            __syncthreads();
+            if (cand) {
+                const float variance = raw.V[lj][li], centerP = raw.P[lj][li];
+                if (s5) {
+                    const int r0 = li - 2, c0 = lj - 2;
+                    float localmin = s.N5[c0][r0];
+#pragma unroll
+                    for (int q = 1; q < 5; ++q) {
+                        const float t = s.N5[c0 + q][r0];
+                        localmin = (t < localmin) ? t : localmin;
+                    }
+                    changed = detect_decide<5>(k, psum, localmin, tree25(s.QV, s.PV2, s.TV, r0, c0), tree25(s.QM, s.PM2, s.TM, r0, c0), centerP, variance,
+                                               tb.y, tb.z, g, c);
+                } else {
+                    const int r0 = li - 1, c0 = lj - 1;
+                    float localmin = s.N3[c0][r0];
+#pragma unroll
+                    for (int q = 1; q < 3; ++q) {
+                        const float t = s.N3[c0 + q][r0];
+                        localmin = (t < localmin) ? t : localmin;
+                    }
+                    changed = detect_decide<3>(k, psum, localmin, tree9s(s.QV, s.PV2, r0, c0), tree9s(s.QM, s.PM2, r0, c0), centerP, variance, tb.y, tb.z, g, c);
+                }
+            }
+        }
+        if (live) {
+            if (changed) {
+                L0[L_GROUND * N2 + cell] = g;
+                L0[L_GROUNDPATCH * N2 + cell] = c;
+            }
+            if (v.skew.sk) {
+                skew_store_cell(v, sp, cell, i, j, g, c, (flags & DTF_FAR) != 0);
+            } else if (v.spiral_recs) {
+                const float d1 = decay_confidence(k, c);
+                float* D1 = v.roll_scratch + (size_t)sp.slot * 2 * k.N2;
+                D1[cell] = d1;
+                if (i == j) D1[k.N2 + cell] = decay_confidence(k, d1);
+            }
+        }
+        __syncthreads();   // the derived arrays and this stage are free again
     }
 }
 
@@ -1962,11 +1986,12 @@ int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int 
 
     static const int detect_occ = getenv("GG_DETECT_OCC") ? atoi(getenv("GG_DETECT_OCC")) : 5;
     const dim3 dgrid(cdiv(v.k.N, DT_X), cdiv(v.k.N, DT_Y), count);
+    const dim3 tgrid(cdiv(v.k.N, DT_X), cdiv(cdiv(v.k.N, DT_Y), DT_TILES), count);
     if (layer_map) {   // TMA-staged tile (needs a 16-byte row pitch: N % 4 == 0)
         if (detect_occ >= 5)
-            GG_LAUNCH(K_DETECT, k_detect_tma<5><<<dgrid, dim3(DT_X, DT_Y), 0, st>>>(v, batch, *layer_map));
+            GG_LAUNCH(K_DETECT, k_detect_tma<5><<<tgrid, dim3(DT_X, DT_Y), 0, st>>>(v, batch, *layer_map));
         else
-            GG_LAUNCH(K_DETECT, k_detect_tma<4><<<dgrid, dim3(DT_X, DT_Y), 0, st>>>(v, batch, *layer_map));
+            GG_LAUNCH(K_DETECT, k_detect_tma<4><<<tgrid, dim3(DT_X, DT_Y), 0, st>>>(v, batch, *layer_map));
     } else if (detect_occ >= 5)
         GG_LAUNCH(K_DETECT, k_detect_ldg<5><<<dgrid, dim3(DT_X, DT_Y), 0, st>>>(v, batch));
     else
@@ -2093,7 +2118,7 @@ __global__ void k_detect_cell(View v, int slot, int i, int j) {
 int launch_detect_only(const View& v, const SlotParams* batch, int count, cudaStream_t st, Profiler* prof, const CUtensorMap* layer_map) {
     const dim3 dgrid(cdiv(v.k.N, DT_X), cdiv(v.k.N, DT_Y), count);
     if (layer_map)
-        GG_LAUNCH(K_DETECT, k_detect_tma<4><<<dgrid, dim3(DT_X, DT_Y), 0, st>>>(v, batch, *layer_map));
+        GG_LAUNCH(K_DETECT, k_detect_tma<4><<<dim3(cdiv(v.k.N, DT_X), cdiv(cdiv(v.k.N, DT_Y), DT_TILES), count), dim3(DT_X, DT_Y), 0, st>>>(v, batch, *layer_map));
     else
         GG_LAUNCH(K_DETECT, k_detect_ldg<4><<<dgrid, dim3(DT_X, DT_Y), 0, st>>>(v, batch));
     return 1;

@@ -31,6 +31,13 @@ int main(int argc, char** argv) {
     node.init();
     std::vector<uint8_t> published;
     int n_published = -1;
+    // image sinks (GroundGridNodelet.cpp:219-228): a colour image of "ground" and the terrain image
+    int n_layer_images = 0, n_terrain_images = 0;
+    size_t layer_image_bytes = 0, terrain_image_bytes = 0;
+    node.layer_pubs_["ground"] = [&](const groundgrid::GroundGridNodelet::LayerImage& im) { ++n_layer_images; layer_image_bytes = im.data.size(); };
+    node.terrain_im_pub_ = [&](const groundgrid::GroundGridNodelet::LayerImage& im) { ++n_terrain_images; terrain_image_bytes = im.data.size(); };
+    std::shared_ptr<sensor_msgs::PointCloud2> last_map_msg;
+    double last_map_odo[3] = {0, 0, 0}, last_map_tmv[7] = {0}, last_map_tmb[7] = {0};
     node.filtered_cloud_pub_ = [&](const sensor_msgs::PointCloud2& m) { published = m.data; n_published = (int)m.width; };
 
     // a cloud before the first odometry must be dropped silently (GroundGridNodelet.cpp:124-125)
@@ -65,6 +72,11 @@ int main(int argc, char** argv) {
         odom->header.frame_id = "map";
         odom->pose.pose.position.x = odo[0]; odom->pose.pose.position.y = odo[1]; odom->pose.pose.position.z = odo[2];
         node.odom_callback(odom);
+        if (frame_is_map) {
+            last_map_msg = msg;
+            for (int q = 0; q < 3; ++q) last_map_odo[q] = odo[q];
+            for (int q = 0; q < 7; ++q) { last_map_tmv[q] = tmv[q]; last_map_tmb[q] = tmb[q]; }
+        }
         n_published = -1;
         node.points_callback(msg);
         if (n_published < 0) { std::fprintf(stderr, "scan %d produced no cloud\n", s); return 3; }
@@ -74,6 +86,63 @@ int main(int argc, char** argv) {
         std::fwrite(G.data(), 4, G.size(), out);
         const grid_map::Matrix& C = (*node.map())["groundpatch"];
         std::fwrite(C.data(), 4, C.size(), out);
+    }
+    {
+        const size_t N = (size_t)node.map()->getSize()(0);
+        if (n_layer_images != n_scans || layer_image_bytes != N * N * 3 || n_terrain_images != n_scans || terrain_image_bytes != N * N * 3 * sizeof(float)) {
+            std::fprintf(stderr, "image sinks: %d / %d images, %zu / %zu bytes\n", n_layer_images, n_terrain_images, layer_image_bytes, terrain_image_bytes);
+            return 3;
+        }
+    }
+    // The reference's public per-phase methods (GroundSegmentation.h:56-62) against filter_cloud: two fresh
+    // GroundGrid + GroundSegmentation pairs, same first odometry, same cloud -- once through filter_cloud, once through
+    // insert_cloud -> detect_ground_patches (4 sections) -> spiral_ground_interpolation; terrain and confidence must agree bit for bit.
+    if (last_map_msg) {
+        pcl::PointCloud<groundgrid::GroundSegmentation::PCLPoint>::Ptr cloud(new pcl::PointCloud<groundgrid::GroundSegmentation::PCLPoint>);
+        pcl::fromROSMsg(*last_map_msg, *cloud);
+        auto odom = std::make_shared<nav_msgs::Odometry>();
+        odom->pose.pose.position.x = last_map_odo[0]; odom->pose.pose.position.y = last_map_odo[1]; odom->pose.pose.position.z = last_map_odo[2];
+        groundgrid::GroundSegmentation::PCLPoint origin{};
+        origin.x = (float)last_map_tmv[0]; origin.y = (float)last_map_tmv[1]; origin.z = (float)last_map_tmv[2];
+        const geometry_msgs::TransformStamped mapToBase = make_tf("map", "base_link", last_map_tmb);
+        groundgrid::GroundGridConfig cfg;
+        ros::NodeHandle nh;
+        groundgrid::GroundGrid gridA, gridB;
+        groundgrid::GroundSegmentation segA, segB;
+        gridA.setGeometryOverride(dim, res, 0, 1u << 19);
+        gridB.setGeometryOverride(dim, res, 0, 1u << 19);
+        segA.init(nh, (size_t)dim, res);
+        segB.init(nh, (size_t)dim, res);
+        segA.setConfig(cfg);
+        segB.setConfig(cfg);
+        auto mapA = gridA.update(odom), mapB = gridB.update(odom);
+        auto outA = segA.filter_cloud(cloud, origin, mapToBase, *mapA);
+        std::vector<std::pair<size_t, grid_map::Index>> point_index, ignored;
+        std::vector<size_t> outliers;
+        segB.insert_cloud(cloud, 0, cloud->points.size(), origin, point_index, ignored, outliers, *mapB);
+        for (unsigned short section = 0; section < 4; ++section) segB.detect_ground_patches(*mapB, section);
+        segB.spiral_ground_interpolation(*mapB, mapToBase);
+        const grid_map::Matrix GA = (*mapA)["ground"], CA = (*mapA)["groundpatch"];
+        const grid_map::Matrix& GB = (*mapB)["ground"];
+        bool same = true;
+        for (size_t q = 0; q < GA.size(); ++q) same = same && (GA.data()[q] == GB.data()[q] || (GA.data()[q] != GA.data()[q] && GB.data()[q] != GB.data()[q]));
+        const grid_map::Matrix& CB = (*mapB)["groundpatch"];
+        for (size_t q = 0; q < CA.size(); ++q) same = same && (CA.data()[q] == CB.data()[q]);
+        // the index lists: kept + ignored + outliers account for every point the output cloud holds (plus border cells)
+        if (!same || point_index.size() + ignored.size() + outliers.size() < outA->points.size() || point_index.empty()) {
+            std::fprintf(stderr, "per-phase methods disagree with filter_cloud (%zu kept, %zu ignored, %zu outliers, %zu out)\n", point_index.size(), ignored.size(),
+                         outliers.size(), outA->points.size());
+            return 3;
+        }
+        try {   // a sub-range is refused (see GroundSegmentation.h)
+            segB.insert_cloud(cloud, 1, cloud->points.size(), origin, point_index, ignored, outliers, *mapB);
+            std::fprintf(stderr, "insert_cloud accepted a sub-range\n");
+            return 3;
+        } catch (std::invalid_argument&) {}
+        // single-cell methods run
+        segB.interpolate_cell(*mapB, 10, 10);
+        segB.detect_ground_patch<3>(*mapB, 10, 10);
+        segB.detect_ground_patch<5>(*mapB, 10, 10);
     }
     // error behaviour: unknown layer -> std::out_of_range like grid_map
     try { (*node.map())["doesNotExist"]; std::fprintf(stderr, "missing layer did not throw\n"); return 3; } catch (std::out_of_range&) {}

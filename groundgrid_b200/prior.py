@@ -32,7 +32,12 @@ def prior_tensor(handle, slot=0):
     ptr = handle.layer_device_ptr("ground", slot)
     ptr_c = handle.layer_device_ptr("groundpatch", slot)
     assert ptr_c == ptr + 4 * n2, "ground and groundpatch must be contiguous"
-    return torch.as_tensor(_DevicePtr(ptr, 2 * n2), device=f"cuda:{torch.cuda.current_device()}")
+    # the tensor lives on the HANDLE's device (not on whatever device happens to be current in this process)
+    dev = getattr(handle, "device", None)
+    if dev is None:
+        dev = torch.cuda.current_device()
+    with torch.cuda.device(dev):
+        return torch.as_tensor(_DevicePtr(ptr, 2 * n2), device=f"cuda:{dev}")
 
 
 def broadcast_prior_tensors(prior, position, src, group=None):
@@ -51,6 +56,8 @@ def broadcast_prior(handle, src, slot=0, group=None):
 
     handle.synchronize()
     prior = prior_tensor(handle, slot)
+    if torch.distributed.get_backend(group) == "nccl":
+        assert prior.device.index == torch.cuda.current_device(), "the process group's device and the handle's device differ"
     pos = torch.tensor(handle.position(slot), dtype=torch.float64, device=prior.device)
     broadcast_prior_tensors(prior, pos, src, group)
     torch.cuda.synchronize()

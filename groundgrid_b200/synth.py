@@ -137,7 +137,16 @@ def lidar_scan(scene, ego_xy=(0.0, 0.0), yaw=0.0, beams=64, elev_deg=(2.0, -24.8
         pts["intensity"] = inten[keep].astype(np.float32)
         pts["ring"] = ring[keep]
         clouds.append(pts)
-    cloud = np.concatenate(clouds) if len(clouds) > 1 else clouds[0]
+    if len(clouds) > 1:
+        # np.concatenate drops the padding of the record dtype: fill a 32-byte-record array field by field instead
+        cloud = np.zeros(sum(len(c) for c in clouds), POINT_DTYPE)
+        at = 0
+        for c in clouds:
+            for f in ("x", "y", "z", "intensity", "ring"):
+                cloud[f][at:at + len(c)] = c[f]
+            at += len(c)
+    else:
+        cloud = clouds[0]
     origin = np.array([ego_xy[0], ego_xy[1], SENSOR_HEIGHT], np.float32)
     return cloud, origin
 
@@ -172,6 +181,39 @@ def base_from_map(ego_x, ego_y, yaw=0.0, base_z=0.0, pitch=0.0):
     R = R_map_from_base.T
     t = -R @ np.array([ego_x, ego_y, base_z])
     return np.concatenate([R, t[:, None]], axis=1)
+
+
+def quat_from_yaw_pitch(yaw=0.0, pitch=0.0):
+    """Quaternion (x, y, z, w) of Rz(yaw) * Ry(pitch)."""
+    cy, sy = math.cos(0.5 * yaw), math.sin(0.5 * yaw)
+    cp, sp = math.cos(0.5 * pitch), math.sin(0.5 * pitch)
+    return np.array([-sy * sp, cy * sp, sy * cp, cy * cp], np.float64)
+
+
+def tf2_matrix(q, t):
+    """Row-major 3x4 [R|t] of a geometry_msgs/Transform exactly as tf2::Matrix3x3::setRotation builds it (same fp64
+    operation order), i.e. what tf2::doTransform applies.  Feeding (q, t) to the reference and this matrix to the C-ABI
+    gives both the same numbers."""
+    x, y, z, w = (float(v) for v in q)
+    d = x * x + y * y + z * z + w * w
+    s = 2.0 / d
+    xs, ys, zs = x * s, y * s, z * s
+    wx, wy, wz = w * xs, w * ys, w * zs
+    xx, xy, xz = x * xs, x * ys, x * zs
+    yy, yz, zz = y * ys, y * zs, z * zs
+    return np.array([[1.0 - (yy + zz), xy - wz, xz + wy, float(t[0])],
+                     [xy + wz, 1.0 - (xx + zz), yz - wx, float(t[1])],
+                     [xz - wy, yz + wx, 1.0 - (xx + yy), float(t[2])]], np.float64)
+
+
+def base_from_map_qt(ego_x, ego_y, yaw=0.0, base_z=0.0, pitch=0.0):
+    """(q, t) of lookupTransform("base_link", "map") as the ROS message carries it, for a base frame at
+    (ego_x, ego_y, base_z) with the given yaw / pitch in the map (the inverse of the base pose)."""
+    q_pose = quat_from_yaw_pitch(yaw, pitch)
+    q = np.array([-q_pose[0], -q_pose[1], -q_pose[2], q_pose[3]])
+    R = tf2_matrix(q, (0.0, 0.0, 0.0))[:, :3]
+    t = -(R @ np.array([ego_x, ego_y, base_z]))
+    return q, t
 
 
 def stream_pose(k, step=1.0, yaw_step_deg=0.5):

@@ -53,39 +53,7 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def quat_from_yaw_pitch(yaw=0.0, pitch=0.0):
-    """Quaternion (x, y, z, w) of Rz(yaw) * Ry(pitch)."""
-    cy, sy = math.cos(0.5 * yaw), math.sin(0.5 * yaw)
-    cp, sp = math.cos(0.5 * pitch), math.sin(0.5 * pitch)
-    # q = qz * qy
-    return np.array([-sy * sp, cy * sp, sy * cp, cy * cp], np.float64)
-
-
-def tf2_matrix(q, t):
-    """Row-major 3x4 [R|t] exactly as tf2::Matrix3x3::setRotation builds it (same fp64 operation order as
-    oracle/ref_shim/tf2_geometry_msgs/tf2_geometry_msgs.h), so that feeding (q, t) to the reference and this
-    matrix to the oracle port / the CUDA path gives the three of them the same numbers."""
-    x, y, z, w = (float(v) for v in q)
-    d = x * x + y * y + z * z + w * w
-    s = 2.0 / d
-    xs, ys, zs = x * s, y * s, z * s
-    wx, wy, wz = w * xs, w * ys, w * zs
-    xx, xy, xz = x * xs, x * ys, x * zs
-    yy, yz, zz = y * ys, y * zs, z * zs
-    return np.array([[1.0 - (yy + zz), xy - wz, xz + wy, float(t[0])],
-                     [xy + wz, 1.0 - (xx + zz), yz - wx, float(t[1])],
-                     [xz - wy, yz + wx, 1.0 - (xx + yy), float(t[2])]], np.float64)
-
-
-def base_from_map_qt(ego_x, ego_y, yaw=0.0, base_z=0.0, pitch=0.0):
-    """(q, t) of lookupTransform("base_link", "map") for a base frame at (ego_x, ego_y, base_z) with the given
-    yaw / pitch in the map: the inverse of the base pose.  t = -R p with R = tf2_matrix(q)."""
-    q_pose = quat_from_yaw_pitch(yaw, pitch)
-    q = np.array([-q_pose[0], -q_pose[1], -q_pose[2], q_pose[3]])
-    R = tf2_matrix(q, (0.0, 0.0, 0.0))[:, :3]
-    t = -(R @ np.array([ego_x, ego_y, base_z]))
-    return q, t
-
+from groundgrid_b200.synth import base_from_map_qt, quat_from_yaw_pitch, tf2_matrix  # noqa: E402,F401  (pose helpers shared with bench.py)
 
 IDENTITY_Q = np.array([0.0, 0.0, 0.0, 1.0])
 

@@ -32,14 +32,24 @@ def to_matrix(t, q):
                      [xz - wy, yz + wx, 1.0 - (xx + yy), t[2]]], np.float64)
 
 
-def test_host_library_builds_and_exports_class_symbols():
-    lib = build_host.build()
-    out = subprocess.run(["nm", "-DC", lib], capture_output=True, text=True).stdout
-    for sym in ("groundgrid::GroundGrid::update(", "groundgrid::GroundGrid::initGroundGrid(", "groundgrid::GroundGrid::setConfig(",
-                "groundgrid::GroundSegmentation::filter_cloud(", "groundgrid::GroundSegmentation::init(",
-                "groundgrid::GroundSegmentation::setConfig(", "groundgrid::GroundGridNodelet::points_callback(",
-                "groundgrid::GroundGridNodelet::odom_callback(", "groundgrid::GroundGridNodelet::onInit("):
-        assert sym in out, sym
+def test_host_libraries_build_with_the_reference_split_and_export_the_class_symbols():
+    """The reference builds three libraries (CMakeLists.txt:96-144): GroundGrid, GroundSegmentation, the nodelet."""
+    build_host.build()
+    want = {
+        build_host.LIB_GRID: ("groundgrid::GroundGrid::update(", "groundgrid::GroundGrid::initGroundGrid(", "groundgrid::GroundGrid::setConfig("),
+        build_host.LIB_SEG: ("groundgrid::GroundSegmentation::filter_cloud(", "groundgrid::GroundSegmentation::init(",
+                             "groundgrid::GroundSegmentation::setConfig(", "groundgrid::GroundSegmentation::insert_cloud(",
+                             "groundgrid::GroundSegmentation::detect_ground_patches(", "groundgrid::GroundSegmentation::spiral_ground_interpolation(",
+                             "groundgrid::GroundSegmentation::interpolate_cell(", "void groundgrid::GroundSegmentation::detect_ground_patch<3>(",
+                             "void groundgrid::GroundSegmentation::detect_ground_patch<5>("),
+        build_host.LIB_NODELET: ("groundgrid::GroundGridNodelet::points_callback(", "groundgrid::GroundGridNodelet::odom_callback(",
+                                 "groundgrid::GroundGridNodelet::onInit(", "groundgrid::GroundGridNodelet::callbackReconfigure("),
+    }
+    for lib, syms in want.items():
+        assert os.path.basename(lib) in ("libgroundgrid_lib.so", "libgroundgrid_groundsegmentation_lib.so", "libgroundgrid_nodelet.so")
+        out = subprocess.run(["nm", "-DC", "--defined-only", lib], capture_output=True, text=True).stdout
+        for sym in syms:
+            assert sym in out, (lib, sym)
 
 
 @pytest.mark.gpu

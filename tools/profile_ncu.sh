@@ -3,7 +3,7 @@
 # 2. (with "full") ncu --set full of one launch of every pipeline kernel (256 scans/launch) -> gpurun_out/<tag>_top.ncu-rep
 tag=${1:-r02a}
 export GG_STREAMS=1
-BENCH="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+BENCH="python bench.py --steps 2 --warmup 3 --pool 2 --no-e2e --no-cpu-baseline --no-extras"
 # one step = 10 launches on one stream (8 for the scan pipeline + 2 for the map roll); skip the warm-up steps
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches.csv \
     -k regex:"k_(rasterize|cell_tiles|cell_place|scatter|cell_stats|detect|spiral|label|roll)" --launch-skip 28 --launch-count 20 \
