@@ -376,7 +376,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=256, help="independent streams (maps) per GPU")
+    ap.add_argument("--streams", type=int, default=444, help="independent streams (maps) per GPU (444 = 3 per SM: the spiral kernel runs one CTA per scan, three per SM)")
     ap.add_argument("--pool", type=int, default=8, help="distinct ego poses / clouds per stream")
     ap.add_argument("--cpu-scans", type=int, default=200, help="scans of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -423,17 +423,27 @@ def main():
         for s in range(S):
             offs[b, s] = total
             total += int(npts[b, s]) * 32
-    host_pool = torch.empty(total, dtype=torch.uint8)
+    # device pool: every cloud of every stream; host pool (pinned, for the end-to-end leg): the first S_E2E poses only
+    S_E2E = min(S, 4)
+    hoffs = np.zeros((B, S_E2E), np.int64)
+    htotal = 0
+    for b in range(B):
+        for s in range(S_E2E):
+            hoffs[b, s] = htotal
+            htotal += int(npts[b, s]) * 32
+    dev_pool = torch.empty(total, dtype=torch.uint8, device="cuda")
+    host_pool = torch.empty(htotal if not args.no_e2e else 1, dtype=torch.uint8)
     if not args.no_e2e:
         host_pool = host_pool.pin_memory()
     hp = host_pool.numpy()
     for b in range(B):
         for s in range(S):
             raw = np.ascontiguousarray(streams[b][s][0]).view(np.uint8).reshape(-1)
-            hp[offs[b, s]:offs[b, s] + raw.size] = raw
-            if b > 0:                                        # only stream 0 is replayed on the CPU later: the pool is the one copy
-                streams[b][s] = (None, streams[b][s][1])     # (keeps 8 ranks x 8 GB of duplicate clouds out of host memory)
-    dev_pool = host_pool.cuda()
+            if s < S_E2E and not args.no_e2e:
+                hp[hoffs[b, s]:hoffs[b, s] + raw.size] = raw
+            dev_pool[int(offs[b, s]):int(offs[b, s]) + raw.size] = torch.from_numpy(raw)
+            if b > 0:                                        # only stream 0 is replayed on the CPU later
+                streams[b][s] = (None, streams[b][s][1])     # (keeps the duplicate clouds of all other streams out of host memory)
     host_labels = torch.zeros((2, B, PCAP), dtype=torch.uint8).pin_memory()   # two sets: batches overlap in the e2e loop
 
     g = capi.GroundGridB200(DIM_M, RES, device=local_rank, n_slots=B, max_points=PCAP, full_layers=False)
@@ -444,7 +454,7 @@ def main():
     for s in range(S):
         descs.append(g.make_descs(list(range(B)), [int(npts[b, s]) for b in range(B)], [streams[b][s][1] for b in range(B)], [0.0] * B))
         dev_ptrs.append([dev_pool.data_ptr() + int(offs[b, s]) for b in range(B)])
-        host_ptrs.append([host_pool.data_ptr() + int(offs[b, s]) for b in range(B)])
+        host_ptrs.append([host_pool.data_ptr() + int(hoffs[b, min(s, S_E2E - 1)]) for b in range(B)])
         xy.append(np.tile(np.array([float(s), 0.0]), (B, 1)))
         Ts.append(np.tile(pose_T(s)[2].reshape(1, 12), (B, 1)))
     lab_ptrs = [[host_labels.data_ptr() + (q * B + b) * PCAP for b in range(B)] for q in range(2)]
@@ -469,7 +479,7 @@ def main():
         """One scan of every stream through the host-buffer call.  overlap: the call is issued in its two halves
         (gg_filter_cloud_batch_begin / _wait), so the clouds of this step cross the bus while the kernels of the
         previous step finish; its labels are complete one step later."""
-        s = pingpong(tstep[0], S)
+        s = pingpong(tstep[0], S_E2E)
         if tstep[0]:
             g.update_pose_batch(slots, xy[s], Ts[s])
         q = tstep[0] & 1
@@ -783,7 +793,8 @@ def main():
         prior_bcast = {"us_per_broadcast": us, "bytes": int(2 * N2 * 4), "gbs": 2 * N2 * 4 / (us * 1e-6) / 1e9, "ranks": world,
                        "what": "dist.broadcast (NCCL) of ground||groundpatch of one map, in place on the handles' device memory, max over ranks",
                        "labels_of_all_ranks_identical": bool(mx.item() == mn.item()), "labels_match_cpu_on_receivers": bool(all_ok),
-                       "checked_with": checked_with}
+                       "checked_with": "none (--no-cpu-baseline)" if args.no_cpu_baseline else
+                                       "oracle port on every receiving rank: prior (ground, groundpatch, position) read back from the GPU, same cloud"}
 
     # ---- CPU baseline: the reference's CPU path replaying stream 0 of rank 0 on this host (bounded sample)
     cpu = None

@@ -40,7 +40,7 @@ int fail(int code, const char* fmt, ...) {
         if (e__ != cudaSuccess) return fail(GG_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
-constexpr int kStreams = 8;   // upper bound; GG_STREAMS (default 4) picks how many are used
+constexpr int kStreams = 8;   // upper bound; GG_STREAMS (default 8) picks how many are used
 constexpr int kRing = 256;
 
 // CUDA-event pairs around every kernel launch while profiling is enabled.
@@ -305,6 +305,9 @@ struct gg_handle_s {
     uint64_t launches = 0;
     std::vector<void*> dev_allocs;
     std::vector<unsigned char> seen_scratch;  // duplicate-slot check of the batch calls
+    cudaEvent_t stagger_ev[kStreams] = {};    // recorded by an even stream before its spiral, awaited by its odd partner
+    bool stagger_armed[kStreams] = {};
+    int stagger = 0;                          // GG_STAGGER (measured on B200: no gain, the bulk kernels leave the spiral no room; off)
     int sched_levels = 0, sched_visits = 0, sched_max = 0;
     bool out_cloud_ready = false;
     // f1: device copy of a PointCloud2 payload, one buffer per stream group (the copy and the unpack kernel of a slot
@@ -486,7 +489,20 @@ int run_scans_grouped(gg_handle h, int count, const gg_scan_desc* scans, int sto
         if (m == 0) continue;
         cudaStream_t st = h->streams[g];
         if ((rc = ring_commit(h, pos, m, st))) return rc;
-        h->launches += gg::launch_scan_pipeline(view, dp, m, max_points, stop_after, st, h->prof, h->have_layer_map ? &h->layer_map : nullptr);
+        // Staggered stream pairs: the spiral is latency bound (a CTA per scan, a few warps per SM), every other kernel
+        // fills the machine.  Stream 2k + 1 starts its scans when stream 2k has reached its spiral, so in steady state the
+        // spirals of one half of the batch run underneath the bulk kernels of the other half instead of all at once.
+        cudaEvent_t after_detect = nullptr;
+        if (h->stagger && h->n_streams > 1 && stop_after == 0) {
+            if ((g & 1) == 0 && g + 1 < h->n_streams) {
+                after_detect = h->stagger_ev[g];
+                h->stagger_armed[g] = true;
+            } else if ((g & 1) == 1 && h->stagger_armed[g - 1]) {
+                GG_CUDA(cudaStreamWaitEvent(st, h->stagger_ev[g - 1], 0));
+                h->stagger_armed[g - 1] = false;
+            }
+        }
+        h->launches += gg::launch_scan_pipeline(view, dp, m, max_points, stop_after, st, h->prof, h->have_layer_map ? &h->layer_map : nullptr, after_detect);
         GG_CUDA(cudaGetLastError());
         if ((rc = ring_release(h, pos, st))) return rc;
     }
@@ -835,14 +851,16 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
         h->n_streams = 1;
         h->streams[0] = static_cast<cudaStream_t>(stream);
     } else {
-        int want = 4;
+        int want = 8;
         if (const char* e = getenv("GG_STREAMS")) want = atoi(e);
+        if (const char* e = getenv("GG_STAGGER")) h->stagger = atoi(e);
         h->n_streams = std::max(1, std::min(std::min(want, kStreams), n_slots));
         for (int i = 0; i < h->n_streams; ++i) GG_CUDA_TRY(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
     }
     GG_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h->h_ring), sizeof(gg::SlotParams) * kRing * S, cudaHostAllocDefault));
     GG_TRY(dev_alloc(h, &h->d_ring, (size_t)kRing * S));
     for (int i = 0; i < kRing; ++i) GG_CUDA_TRY(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < kStreams; ++i) GG_CUDA_TRY(cudaEventCreateWithFlags(&h->stagger_ev[i], cudaEventDisableTiming));
     h->launches += gg::launch_build_detect_table(v, h->detect_tab, h->streams[0]);
     GG_CUDA_TRY(cudaGetLastError());
     GG_CUDA_TRY(cudaStreamSynchronize(h->streams[0]));
@@ -862,6 +880,8 @@ int gg_destroy(gg_handle h) {
         if (h->d_raw[g]) cudaFree(h->d_raw[g]);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     for (cudaEvent_t e : h->slot_ev) cudaEventDestroy(e);
+    for (int i = 0; i < kStreams; ++i)
+        if (h->stagger_ev[i]) cudaEventDestroy(h->stagger_ev[i]);
     for (int e = 0; e < 2; ++e)
         if (h->batch_done[e]) cudaEventDestroy(h->batch_done[e]);
     for (int e = 0; e < 8; ++e)

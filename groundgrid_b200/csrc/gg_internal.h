@@ -170,8 +170,9 @@ int launch_build_detect_table(const View& v, float4* tab, cudaStream_t st);
 int launch_roll(const View& v, const SlotParams* batch, int count, cudaStream_t st, Profiler* prof);
 // layer_map: TMA descriptor of the handle's layer arena as a 3-D tensor (i, j, slot * n_layers + layer), box
 // 40 x 12 x 1 (k_detect_tma); null -> the patch detection stages its tile with plain loads (N % 4 != 0)
+// after_detect (may be null): recorded on st right before the spiral kernel
 int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int max_points, int stop_after, cudaStream_t st,
-                         Profiler* prof, const CUtensorMap* layer_map);
+                         Profiler* prof, const CUtensorMap* layer_map, cudaEvent_t after_detect);
 // single phases / single cells (the reference's public per-phase methods)
 int launch_detect_only(const View& v, const SlotParams* batch, int count, cudaStream_t st, Profiler* prof, const CUtensorMap* layer_map);
 int launch_spiral_only(const View& v, const SlotParams* batch, int count, cudaStream_t st, Profiler* prof);

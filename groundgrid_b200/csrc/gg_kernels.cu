@@ -1963,7 +1963,7 @@ int launch_roll(const View& v, const SlotParams* batch, int count, cudaStream_t 
 }
 
 int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int max_points, int stop_after, cudaStream_t st,
-                         Profiler* prof, const CUtensorMap* layer_map) {
+                         Profiler* prof, const CUtensorMap* layer_map, cudaEvent_t after_detect) {
     int launches = 0;
     const int nb = max(1, cdiv(max_points, RASTER_TILE));
 
@@ -1997,6 +1997,7 @@ int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int 
     else
         GG_LAUNCH(K_DETECT, k_detect_ldg<4><<<dgrid, dim3(DT_X, DT_Y), 0, st>>>(v, batch));
     ++launches;
+    if (after_detect) cudaEventRecord(after_detect, st);   // the spiral (few warps per SM, latency bound) starts here: see gg_capi.cu
     if (stop_after == 2) return launches;
 
     if (v.skew.sk) {

@@ -15,6 +15,6 @@ python - <<PY
 import json
 d=json.load(open('gpurun_out/${tag}_bench.json'))
 print('value',round(d['value'],1),'ms',round(d['ms_per_step'],4),'e2e',round(d['e2e']['value'],1) if d.get('e2e') else None, 'path frac', round(d['roofline_path']['frac'],4))
-print(d['roofline']['kernel_avg_launch_us'])
+print({k: v['avg_launch_us'] for k, v in d['roofline'].get('per_kernel', {}).items()})
 print(d['single_stream'])
 PY
