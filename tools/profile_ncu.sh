@@ -10,7 +10,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
     $BENCH > gpurun_out/${tag}_launches_bench.log 2>&1
 if [ "$2" = "full" ]; then
 timeout 900 ncu --set full --clock-control none --import-source on -f -o gpurun_out/${tag}_top \
-    -k regex:"k_(rasterize|cell_tiles|cell_place|scatter|cell_stats|detect|spiral_skew|label|roll_gather)" --launch-skip 38 --launch-count 10 \
+    -k regex:"k_(rasterize|cell_tiles|cell_place|scatter|cell_stats|detect|spiral_skew|label|roll_gather)" --launch-skip 35 --launch-count 9 \
     $BENCH > gpurun_out/${tag}_top_bench.log 2>&1
 fi
 ls -la gpurun_out/${tag}_*
