@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the CPU arm of
 bench.py (cpu_baseline / --impl reference).  Nothing under groundgrid_b200/ imports it.
-PARITY UNPINNED -- see the header of gg_oracle.cpp.
+Pinned by oracle/_ref (the unmodified reference sources on CPU stand-ins, oracle/ref.py) -- see the header of gg_oracle.cpp.
 """
 import ctypes as C
 import os

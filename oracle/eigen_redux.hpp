@@ -14,8 +14,8 @@
 //     : redux(start, len/2) + redux(start + len/2, len - len/2)
 // over the block's coefficients in column-major order of the BLOCK
 // (coeff k = block(k % S, k / S), i.e. row index fastest).
-// PARITY UNPINNED: restated from the published Eigen 3.3.7 sources; Eigen >= 3.4 may
-// choose a different traversal for the 5x5 case.
+// Restated from the published Eigen 3.3.7 sources (Eigen >= 3.4 may choose a different traversal for the 5x5 case,
+// SURVEY.md App. A.0); oracle/ref_shim/Eigen/Core, which the unmodified reference is compiled against, states the same order.
 #pragma once
 
 namespace ggo {

@@ -7,16 +7,15 @@
 // --impl reference).  The product (groundgrid_b200/csrc, groundgrid_b200/host) never
 // includes, links or calls anything in oracle/.
 //
-// PARITY UNPINNED: the reference repository has no tests, golden vectors or fixtures
-//  and cannot be built here (no Eigen / grid_map / PCL / ROS in the
-// image, no network), so this oracle is pinned only by (1) hand-checkable
-// known-answer cases in tests/test_oracle_known_answers.py, (2) the committed vectors of
-// tests/golden/, which come from the independent pure-Python restatement tests/pyref.py
-// (NOT from the reference), and (3) a line-by-line reading of the reference sources
-// cited on every function below.  It DEFINES parity as
-// the reference's thread_count = 1 execution (the shipped thread_count = 8 has data
-// races, GroundSegmentation.cpp:99-109 vs :234,282-309), with Eigen-3.3.7 reduction
-// order (eigen_redux.hpp) and grid_map_core 1.6.x geometry (gridmap_semantics.hpp).
+// PINNED BY THE REFERENCE ITSELF: the reference repository has no tests, golden vectors or fixtures (SURVEY.md
+// section 4 / 8c), but its two source files of this path compile unmodified against CPU stand-ins
+// (oracle/build_ref.py -> oracle/_ref/libgg_ref.so, see oracle/ref_harness.cpp).  tests/test_oracle_vs_ref.py
+// demands that this port and that library agree bit for bit (every layer, label, output position, map roll) on the
+// BASELINE configurations, rolling streams with outliers, random geometries / configs; tests/golden/ holds vectors
+// produced by the reference library.  What the stand-ins restate from published third-party sources -- Eigen 3.3.7's
+// reduction order, grid_map_core 1.6.x geometry, tf2's point transform -- is restated here in the same way
+// (eigen_redux.hpp, gridmap_semantics.hpp).  Parity is DEFINED as the reference's thread_count = 1 execution (the
+// shipped thread_count = 8 has data races, GroundSegmentation.cpp:99-109 vs :234,282-309).
 //
 // Build: see oracle/Makefile  (g++ -O3 -DNDEBUG -std=c++17 -ffp-contract=off).
 // =====================================================================================

@@ -12,7 +12,8 @@
 //   getPosition   <- src/GroundGrid.cpp:125
 //   getIndex      <- src/GroundSegmentation.cpp:228,261
 //   isInside      <- src/GroundSegmentation.cpp:230
-// PARITY UNPINNED: no golden vectors exist for these.
+// tests/test_oracle_vs_ref.py checks these against the CPU GridMap the unmodified reference is compiled with
+// (oracle/ref_shim/grid_map_core/GridMap.hpp, restated from the same published sources).
 #pragma once
 #include <cmath>
 #include <cstdint>
