@@ -2015,6 +2015,12 @@ int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int 
         const int threads = 4 * vs.skew.M + SKEW_IRR_THREADS;
         const size_t shm = (size_t)SKEW_RING * v.skew.irr_chunks * sizeof(uint4) + (size_t)2 * v.skew.lanes * sizeof(float2) +
                            (size_t)v.skew.irr_max * 9 * sizeof(float2) + (size_t)v.skew.irr_max * sizeof(float) + 16;
+        if (shm > 48 * 1024) {   // very large maps (N > ~1500): opt in to more dynamic shared memory
+            cudaFuncSetAttribute(k_spiral_skew<320, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+            cudaFuncSetAttribute(k_spiral_skew<448, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+            cudaFuncSetAttribute(k_spiral_skew<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+            cudaFuncSetAttribute(k_spiral_skew<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        }
         if (threads <= 320)       // time-shared lane threads (GG_SPIRAL_M): several scans share an SM
             GG_LAUNCH(K_SPIRAL, (k_spiral_skew<320, 3><<<count, threads, shm, st>>>(vs, batch)));
         else if (threads <= 448)
@@ -2027,6 +2033,7 @@ int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int 
         const size_t shm = (size_t)((v.levels + 4) & ~3) * sizeof(int) + (size_t)(v.spiral_dist + 1) * v.spiral_threads * sizeof(float2);
 #define GG_SPIRAL_CASE(T, D)                                                                      \
     if (v.spiral_threads == T && v.spiral_dist == D) {                                            \
+        if (shm > 48 * 1024) cudaFuncSetAttribute(k_spiral_pipe<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm); \
         GG_LAUNCH(K_SPIRAL, k_spiral_pipe<T, D><<<count, T, shm, st>>>(v, batch));                \
     }
         GG_SPIRAL_CASE(512, 1)

@@ -411,3 +411,27 @@ def test_packer_pool_ring_claims_and_cancel(threads, n_jobs, n_points, ring, rou
     f.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int]
     for _ in range(3):
         assert f(threads, n_jobs, n_points, ring, rounds, lag) == 0
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (no GPU involved): one JSON line with impl = reference, the metric / unit of the GPU arm, a
+    cpu_baseline describing the run and an e2e object repeating the value; it runs the reference's own sources (oracle/_ref)
+    whenever that library is available."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--pool", "2"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Mpoints/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    from oracle import ref as refmod
+
+    assert d["cpu_baseline"]["kind"] == ("reference" if refmod.available() else "port")
