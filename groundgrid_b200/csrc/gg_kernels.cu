@@ -971,6 +971,8 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 
 constexpr int DT_HX = 4;                 // halo in i of the TMA tile (alignment of the box start)
 constexpr int DT_WT = DT_X + 2 * DT_HX;  // 40
+constexpr int DT_WC = DT_WT - 4;         // 36: columns that can be the first row of a 3 / 5-row window
+constexpr int DT_WB = DT_WT - 2;         // 38: columns whose product is read by some window
 
 struct __align__(128) DetectRaw {   // one pipeline stage: the three TMA destinations
     float P[DT_R][DT_WT];   // kept points per cell
@@ -1019,12 +1021,17 @@ __device__ __forceinline__ bool detect_decide(const Const& k, float psum, float 
     if ((double)oc > 0.5 && (double)groundlevel >= __dadd_rn((double)og, k.outlier_tol)) return false;
     if ((double)vt > __dmul_rn((double)maxVar, (double)maxVar) && maxVar > 0.0f &&
         (double)psum > __dmul_rn((double)__fmul_rn(__fmul_rn(groundDiff, e), (float)S), k.gp_thresh)) {
-        const double ncd = __ddiv_rn((double)psum, k.occ_factor);
-        const float nc = (float)((1.0 < ncd) ? 1.0 : ncd);  // std::min(ncd, 1.0)
+        // std::min(psum / factor, 1.0): a quotient of at least one needs no division (psum >= factor > 0 <=> quotient >= 1)
+        float nc = 1.0f;
+        if (!(k.occ_factor > 0.0 && (double)psum >= k.occ_factor)) {
+            const double ncd = __ddiv_rn((double)psum, k.occ_factor);
+            nc = (float)((1.0 < ncd) ? 1.0 : ncd);
+        }
         const float num = __fadd_rn(__fmul_rn(groundlevel, nc), __fmul_rn(__fmul_rn(oc, og), 2.0f));
         const float den = __fadd_rn(nc, __fmul_rn(oc, 2.0f));
         g = __fdiv_rn(num, den);
-        const double cd = __ddiv_rn(__dadd_rn(__ddiv_rn((double)psum, k.occ_factor2), (double)oc), 2.0);
+        // std::min((psum / (factor * 2.0f) + oc) / 2.0, 1.0): halving is exact (x * 0.5)
+        const double cd = __dmul_rn(__dadd_rn(__ddiv_rn((double)psum, k.occ_factor2), (double)oc), 0.5);
         c = (float)((1.0 < cd) ? 1.0 : cd);
         return true;
     }
@@ -1091,11 +1098,12 @@ __global__ void __launch_bounds__(DT_X* DT_Y, MIN_BLOCKS) k_detect_tma(View v, c
         mbar_wait(&s_bar[kk & 1], (uint32_t)((kk >> 1) & 1));
 
         // stage A: column partials of the point counts (exact) -- positions p = tid, tid + 256 of the 12 x 40 tile
-        for (int p = tid; p < DT_R * DT_WT; p += DT_X * DT_Y) {
-            const int row = p / DT_WT, col = p % DT_WT;   // row = j index of the tile, col = i index
+        // (only columns 0 .. 35 are ever the first row of a window: col + 4 <= 39 stays inside the tile, no bounds tests)
+        for (int p = tid; p < DT_R * DT_WC; p += DT_X * DT_Y) {
+            const int row = p / DT_WC, col = p % DT_WC;   // row = j index of the tile, col = i index
             float a[5];
 #pragma unroll
-            for (int q = 0; q < 5; ++q) a[q] = (col + q < DT_WT) ? raw.P[row][col + q] : 0.0f;
+            for (int q = 0; q < 5; ++q) a[q] = raw.P[row][col + q];
             const float c3 = __fadd_rn(__fadd_rn(a[0], a[1]), a[2]);
             s.C3[row][col] = c3;
             s.C5[row][col] = __fadd_rn(__fadd_rn(c3, a[3]), a[4]);
@@ -1119,15 +1127,17 @@ __global__ void __launch_bounds__(DT_X* DT_Y, MIN_BLOCKS) k_detect_tma(View v, c
         bool changed = false;
         if (any) {
             // stage B: products, pairs, triples and column minima
-            for (int p = tid; p < DT_R * DT_WT; p += DT_X * DT_Y) {
-                const int row = p / DT_WT, col = p % DT_WT;
+            // (products are needed up to column 37 -- the last row of the right-most window --, pairs up to 36, the rest up
+            // to 35; reads of columns 40 / 41 for those two extra columns stay inside this struct and feed unused entries)
+            for (int p = tid; p < DT_R * DT_WB; p += DT_X * DT_Y) {
+                const int row = p / DT_WB, col = p % DT_WB;
                 float qv[3], qm[3], m[5];
 #pragma unroll
-                for (int q = 0; q < 5; ++q) m[q] = (col + q < DT_WT) ? raw.M[row][col + q] : FLT_MAX;
+                for (int q = 0; q < 5; ++q) m[q] = raw.M[row][col + q];
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
-                    const float pp = (col + q < DT_WT) ? raw.P[row][col + q] : 0.0f;
-                    const float vv = (col + q < DT_WT) ? raw.V[row][col + q] : 0.0f;
+                    const float pp = raw.P[row][col + q];
+                    const float vv = raw.V[row][col + q];
                     qv[q] = __fmul_rn(pp, vv);
                     qm[q] = __fmul_rn(pp, m[q]);
                 }
