@@ -122,7 +122,7 @@ struct View {
     unsigned long long* cnt64;  // [n_slots][N2] runs of the cell << 32 | kept points of the cell (one atomic per run)
     int* raw_i;           // [n_slots][N2] inside points per cell (full layers)
     int* cellstart;       // [n_slots][N2] exclusive scan of the per-cell point counts
-    int* worklist;        // [n_slots][N2] non-empty cells grouped by count class, heaviest first (k_scan_cells)
+    int4* worklist;       // [n_slots][N2] non-empty cells grouped by count class, heaviest first: (cell, points, runs, segment start)
     int* wl_count;        // [n_slots][2] entries of the worklist, kept points of the scan
     int* cell_agg;        // [n_slots][cell_tiles][65] per tile of 4096 cells: cells per count class, kept points
     int cell_tiles;       // ceil(N2 / 4096)

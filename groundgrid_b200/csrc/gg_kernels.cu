@@ -391,8 +391,8 @@ constexpr int CELL_TILE = 4096;      // CT_THREADS threads x CT_PER cells
 constexpr int CT_THREADS = 256, CT_PER = 16;
 constexpr int AGG_STRIDE = WL_CLASSES + 1;   // [0, WL_CLASSES): cells per class, [WL_CLASSES]: kept points
 
-// 16 consecutive cells per thread: eight 16-byte loads of the (runs << 32 | points) counters, low words kept
-__device__ __forceinline__ void load_tile_counts(const unsigned long long* cnt64, int N2, int cell0, int c[CT_PER]) {
+// 16 consecutive cells per thread: eight 16-byte loads of the (runs << 32 | points) counters; c = points, r (optional) = runs
+__device__ __forceinline__ void load_tile_counts(const unsigned long long* cnt64, int N2, int cell0, int c[CT_PER], int* r = nullptr) {
     if (cell0 + CT_PER <= N2 && (((size_t)cnt64 & 15) == 0) && (cell0 & 1) == 0) {
         const ulonglong2* p = reinterpret_cast<const ulonglong2*>(cnt64 + cell0);
 #pragma unroll
@@ -400,10 +400,18 @@ __device__ __forceinline__ void load_tile_counts(const unsigned long long* cnt64
             const ulonglong2 v = p[q];
             c[2 * q] = (int)(uint32_t)v.x;
             c[2 * q + 1] = (int)(uint32_t)v.y;
+            if (r) {
+                r[2 * q] = (int)(v.x >> 32);
+                r[2 * q + 1] = (int)(v.y >> 32);
+            }
         }
     } else {
 #pragma unroll
-        for (int q = 0; q < CT_PER; ++q) c[q] = (cell0 + q < N2) ? (int)(uint32_t)cnt64[cell0 + q] : 0;
+        for (int q = 0; q < CT_PER; ++q) {
+            const unsigned long long v = (cell0 + q < N2) ? cnt64[cell0 + q] : 0ull;
+            c[q] = (int)(uint32_t)v;
+            if (r) r[q] = (int)(v >> 32);
+        }
     }
 }
 
@@ -437,8 +445,8 @@ __global__ void __launch_bounds__(CT_THREADS) k_cell_place(View v, const SlotPar
     const int* agg = v.cell_agg + (size_t)sp.slot * tiles * AGG_STRIDE;
     const size_t off = (size_t)sp.slot * N2;
     const int cell0 = tile * CELL_TILE + tid * CT_PER;
-    int c[CT_PER];
-    load_tile_counts(v.cnt64 + off, N2, cell0, c);
+    int c[CT_PER], rn[CT_PER];
+    load_tile_counts(v.cnt64 + off, N2, cell0, c, rn);
     // one warp: per class (2 per lane) the total over all tiles and the part of the earlier tiles
     if (warp == 0) {
         int tot[2] = {0, 0}, pre[2] = {0, 0};
@@ -480,13 +488,14 @@ __global__ void __launch_bounds__(CT_THREADS) k_cell_place(View v, const SlotPar
     __syncthreads();
     int run = s_cur[WL_CLASSES] + incl - sum;
     for (int w = 0; w < warp; ++w) run += s_warp[w];
-    int* wl = v.worklist + off;
+    // a worklist entry carries everything k_cell_stats needs to start on the cell: (cell, points, runs, segment start)
+    int4* wl = v.worklist + off;
     int cs[CT_PER];
 #pragma unroll
     for (int q = 0; q < CT_PER; ++q) {
         cs[q] = run;
+        if (c[q] > 0) wl[atomicAdd(&s_cur[worklist_class(c[q])], 1)] = make_int4(cell0 + q, c[q], rn[q], run);
         run += c[q];
-        if (c[q] > 0) wl[atomicAdd(&s_cur[worklist_class(c[q])], 1)] = cell0 + q;
     }
     if (cell0 + CT_PER <= N2 && (N2 & 3) == 0) {
         int4* dst = reinterpret_cast<int4*>(v.cellstart + off + cell0);
@@ -596,10 +605,8 @@ __global__ void __launch_bounds__(CS_THREADS, FULL ? 2 : 4) k_cell_stats(View v,
     const int wl_n = v.wl_count[2 * sp.slot];
     const float oz = sp.oz;
     for (int t = gt; t < wl_n; t += gridDim.x * CS_THREADS) {
-    const int cell = v.worklist[coff + t];
-    const unsigned long long cnt_runs = v.cnt64[coff + cell];
-    const int cnt = (int)(uint32_t)cnt_runs, runs = (int)(cnt_runs >> 32);
-    const int cstart = v.cellstart[coff + cell];
+    const int4 entry = v.worklist[coff + t];   // one load instead of a chain of three dependent ones
+    const int cell = entry.x, cnt = entry.y, runs = entry.z, cstart = entry.w;
     const float* zs = v.zsorted + (size_t)sp.slot * v.pcap + cstart;
     uint2* dir = v.rundir + (size_t)sp.slot * v.pcap + cstart;
     // the kernel is bound by the latency of dependent global loads: pull the first lines of the segment and of the
