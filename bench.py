@@ -256,7 +256,7 @@ def reference_arm(args, rank, world):
         "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
         "config": {"workload": f"{workers} independent SemanticKITTI-shaped synthetic 64-beam streams (one per host core), "
                                f"~120k pts/scan, {N_CELLS}x{N_CELLS} @ {RES} m; step = one scan of every stream (update + filter_cloud) "
-                               f"on {what} (thread_count=1 per stream); the GPU arm runs 256 streams of the same shape per GPU",
+                               f"on {what} (thread_count=1 per stream); the GPU arm runs {args.streams} streams of the same shape per GPU",
                    "streams": workers, "points_per_step": pts_per_step},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind,
                          "sample": f"{steps} steps x {workers} scans after {args.warmup} warm-up steps"},

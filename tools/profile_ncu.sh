@@ -1,6 +1,6 @@
 # usage (on the GPU box, one GPU): bash tools/profile_ncu.sh <tag> [full]
 # 1. launch list of bench.py's step (all kernels, gpu__time_duration only)   -> gpurun_out/<tag>_launches.csv
-# 2. (with "full") ncu --set full of one launch of every pipeline kernel (256 scans/launch) -> gpurun_out/<tag>_top.ncu-rep
+# 2. (with "full") ncu --set full of one whole step (same filter and window as the launch list: the 10 launches of the first timed step) -> gpurun_out/<tag>_top.ncu-rep
 tag=${1:-r02a}
 export GG_STREAMS=1
 BENCH="python bench.py --steps 2 --warmup 3 --pool 2 --no-e2e --no-cpu-baseline --no-extras"
@@ -10,7 +10,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
     $BENCH > gpurun_out/${tag}_launches_bench.log 2>&1
 if [ "$2" = "full" ]; then
 timeout 900 ncu --set full --clock-control none --import-source on -f -o gpurun_out/${tag}_top \
-    -k regex:"k_(rasterize|cell_tiles|cell_place|scatter|cell_stats|detect|spiral_skew|label|roll_gather)" --launch-skip 35 --launch-count 9 \
+    -k regex:"k_(rasterize|cell_tiles|cell_place|scatter|cell_stats|detect|spiral|label|roll)" --launch-skip 28 --launch-count 10 \
     $BENCH > gpurun_out/${tag}_top_bench.log 2>&1
 fi
 ls -la gpurun_out/${tag}_*
