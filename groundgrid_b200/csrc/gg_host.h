@@ -31,7 +31,25 @@ struct SkewTables {
     std::vector<uint32_t> irr_recs;      // 16 words per irregular visit: own, nb[9], recents01, recents23, mirror, lane, cell, pad
     int max_irr_per_level = 0;
     size_t n_regular = 0, n_irregular = 0;
+    // every visit in SEQUENTIAL order with the memory it touches in k_spiral_skew (input of build_skew_sync)
+    struct Access {
+        int level, lane;          // lane = side * KP + ring + 1 (also the visit's exchange-buffer entry)
+        int own, mirror, cell;    // slots written (mirror: -1 or the second home of a ring corner), cell of the normal layers
+        int nb[9];                // slots read
+        int recent_lane[9];       // >= 0: neighbour q was written one level ago and arrives through the exchange buffer entry of this lane
+        bool regular;             // executed by its lane thread (else by the irregular warps)
+    };
+    std::vector<Access> acc;
 };
+// Point-to-point synchronisation of k_spiral_skew<.., ASYNC>: the CTA-wide barrier per level is replaced by progress
+// counters, one per AGENT (a warp of lane threads, or the two irregular warps together).  req[(agent * levels + l) * 32 + b]
+// = progress agent b must have reached (= number of levels it has completed) before `agent` may start level l.
+// Derived from the exact read / write sets of every visit (RAW, WAR and WAW on the skewed copy, the normal layers and
+// the exchange ring of depth xch_depth), with the kernel's timing: the slots of a visit at level l are loaded during
+// level l - 1, neighbours written at level l - 1 are read from the exchange ring during level l, stores happen at level l.
+// M = lane threads per side (thread layout).  Returns false if some dependence cannot be expressed (then the barrier
+// kernel is used).
+bool build_skew_sync(const SkewTables& t, int M, int xch_depth, std::vector<uint16_t>& req, int& n_agents);
 void build_spiral_skew(int n, const std::vector<int>& level_start, const std::vector<uint32_t>& visits, SkewTables& t);
 bool build_spiral_records(int n, double res_sq, const std::vector<int>& level_start, const std::vector<uint32_t>& visits,
                           int dist, std::vector<uint32_t>& recs, int& max_recent);
@@ -47,5 +65,6 @@ int gg_host_move_map(double res, double* pos_xy, double nx, double ny, int* shif
 int gg_host_pack_cloud(const gg_point* src, size_t n, unsigned char* dst);
 int gg_host_pack_cloud_cached(const gg_point* src, size_t n, unsigned char* dst);
 int gg_host_packer_selftest(int threads, int n_jobs, size_t n_points, int ring_slots, int rounds, int lag);
+int gg_host_spiral_skew_sync(int n, int M, int xch_depth, uint16_t* req, int req_cap, int* n_agents);
 int gg_host_spiral_skew(int n, int* header, int* pattern, int* lane_begin, int* lane_end, int* cell_home, int* irr_level_start, uint32_t* irr_recs, int irr_cap_words);
 }

@@ -93,6 +93,11 @@ struct SkewView {
     const int* thr_ph_end;
     const int* thr_ph_cell0;
     int thr_M, thr_phases;
+    // point-to-point synchronisation tables of the two layouts (gg_host.cpp:build_skew_sync), nullptr: CTA barrier per level
+    //   [agent][level][32] progress agent b must have reached before `agent` starts the level
+    const uint16_t* req;
+    const uint16_t* thr_req;
+    int sync_sleep;         // ns a waiting warp sleeps between two looks at the progress counters (0: spin)
     // irregular visits, one fixed-size block per level (irr_chunks x uint4):
     //   words [ (v * 9 + q) * 2 + {0, 1} ] = slot of neighbour q of visit v, producer lane if it was
     //                                        written one level ago (else 0xffffffff)

@@ -1439,9 +1439,35 @@ constexpr int SKEW_STAGE_LEAD = 10;  // a block is staged this many levels befor
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-template <int SIDE>
-__device__ __forceinline__ void skew_lane_thread(const View& v, const SlotParams& sp, float2* s_xch) {
+// ---- point-to-point synchronisation (ASYNC variants) ---------------------------------------
+// Instead of one CTA barrier per level every AGENT (a warp of lane threads; the two irregular warps together) publishes
+// the number of levels it has completed in shared memory and, before a level, waits until the agents it depends on have
+// reached the progress the host table asks for (gg_host.cpp:build_skew_sync: exact RAW / WAR / WAW sets of the level's
+// visits).  Neighbouring rings trail each other by three levels, so most requirements leave a level of slack: a warp
+// that is late (a cache miss, a lost issue slot) no longer stalls the whole CTA.  Lane b of a warp watches agent b.
+constexpr int SKEW_XCH_ASYNC = 4;    // depth of the exchange ring of the ASYNC variants (the barrier variant needs 2)
+__device__ __forceinline__ void skew_publish(int* s_prog, int agent, int completed, int lane) {
+    __syncwarp();
+    if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(s_prog + agent)), "r"(completed) : "memory");
+}
+__device__ __forceinline__ void skew_wait(const int* s_prog, int need, int lane, int sleep_ns) {
+    const uint32_t addr = smem_u32(s_prog + lane);
+    for (;;) {
+        int p;
+        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(p) : "r"(addr) : "memory");
+        if (__all_sync(0xffffffffu, p >= need)) break;
+        if (sleep_ns) __nanosleep(sleep_ns);
+    }
+}
+
+template <int SIDE, bool ASYNC>
+__device__ __forceinline__ void skew_lane_thread(const View& v, const SlotParams& sp, float2* s_xch, int* s_prog) {
     const SkewView& w = v.skew;
+    constexpr int XM = (ASYNC ? SKEW_XCH_ASYNC : 2) - 1;   // exchange ring: entry of level l is [l & XM]
+    const int lane_id = threadIdx.x & 31;
+    const int agent = threadIdx.x >> 5;
+    const uint16_t* __restrict__ req = ASYNC ? w.req + (size_t)agent * w.levels * 32 + lane_id : nullptr;
+    int need_nxt = ASYNC ? (int)__ldg(req) : 0;   // requirement of the next level this warp executes, loaded one level ahead
     constexpr int PQ = SIDE == 0 ? 1 : (SIDE == 1 ? 3 : (SIDE == 2 ? 7 : 5));  // neighbour index of the lane's previous cell
     constexpr int PF_FAR = 8, PF_NEAR = 2;
     const int L = w.levels, KP = w.KP, lanes = w.lanes, M = w.M;
@@ -1502,6 +1528,11 @@ __device__ __forceinline__ void skew_lane_thread(const View& v, const SlotParams
 #define GG_LANE_LEVEL(l_, CUR, CURD, NXT, NXTD)                                                      \
     {                                                                                               \
         const int l__ = (l_);                                                                       \
+        if (ASYNC) {                                                                                \
+            const int need__ = need_nxt;                                                            \
+            if (l__ + 1 < L) need_nxt = (int)__ldg(req + (size_t)(l__ + 1) * 32);                   \
+            skew_wait(s_prog, need__, lane_id, w.sync_sleep);                                                     \
+        }                                                                                           \
         if (l__ + PF_FAR >= lb && l__ + PF_FAR < le) {                                              \
             prefetch_l2(SK + (base0 + (l__ + PF_FAR) * KP + off_new));                              \
             prefetch_l2(SD + (base0 + (l__ + PF_FAR) * KP));                                        \
@@ -1516,14 +1547,17 @@ __device__ __forceinline__ void skew_lane_thread(const View& v, const SlotParams
             NXTD = SD[base0 + (l__ + 1) * KP];                                                      \
         }                                                                                           \
         if (l__ >= lb && l__ < le) {                                                                \
-            CUR[PQ] = s_xch[((l__ + 1) & 1) * lanes + xid];                                         \
+            CUR[PQ] = s_xch[((l__ - 1) & XM) * lanes + xid];                                        \
             const float2 r__ = spiral_visit(CUR, CURD);                                             \
-            s_xch[(l__ & 1) * lanes + xid] = r__;                                                   \
+            s_xch[(l__ & XM) * lanes + xid] = r__;                                                  \
             SK[base0 + l__ * KP] = r__;                                                             \
             Gn[cell0 + l__ * cstep] = r__.x;                                                        \
             if (CURD >= 0.0f) Cn[cell0 + l__ * cstep] = r__.y;                                      \
         }                                                                                           \
-        __syncthreads();                                                                            \
+        if (ASYNC)                                                                                  \
+            skew_publish(s_prog, agent, l__ + 1, lane_id);                                          \
+        else                                                                                        \
+            __syncthreads();                                                                        \
     }
     for (int l = 0; l < L; l += 2) {
         // done with this ring: move on to ring + M (it starts well after this one ended)
@@ -1538,8 +1572,13 @@ __device__ __forceinline__ void skew_lane_thread(const View& v, const SlotParams
         // a warp (32 consecutive rings of one side) has work only in a window of levels; outside of it
         // the per-level cost must be the barrier alone (the level time is set by instruction issue)
         if (l < w_first || l >= w_last) {
-            __syncthreads();
-            if (l + 1 < L) __syncthreads();
+            if (ASYNC) {   // nothing to do and nothing to wait for: the warp has "completed" both levels
+                skew_publish(s_prog, agent, min(l + 2, L), lane_id);
+                if (l + 2 < L) need_nxt = (int)__ldg(req + (size_t)(l + 2) * 32);
+            } else {
+                __syncthreads();
+                if (l + 1 < L) __syncthreads();
+            }
             continue;
         }
         GG_LANE_LEVEL(l, A, dA, B, dB)
@@ -1550,9 +1589,15 @@ __device__ __forceinline__ void skew_lane_thread(const View& v, const SlotParams
 
 __device__ __forceinline__ void skew_named_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(SKEW_IRR_THREADS) : "memory"); }
 
-__device__ __forceinline__ void skew_irregular_thread(const View& v, const SlotParams& sp, float2* s_xch, uint4* s_ring, float2* s_nb, float* s_dd) {
+template <bool ASYNC>
+__device__ __forceinline__ void skew_irregular_thread(const View& v, const SlotParams& sp, float2* s_xch, uint4* s_ring, float2* s_nb, float* s_dd, int* s_prog) {
     const SkewView& w = v.skew;
     const int ti = threadIdx.x - 4 * w.M;  // 0 .. 63
+    constexpr int XM = (ASYNC ? SKEW_XCH_ASYNC : 2) - 1;
+    const int lane_id = threadIdx.x & 31;
+    const int agent = 4 * w.M / 32;        // both warps form one agent
+    const uint16_t* __restrict__ req = ASYNC ? w.req + (size_t)agent * w.levels * 32 + lane_id : nullptr;
+    int need_nxt = ASYNC ? (int)__ldg(req) : 0;
     const int L = w.levels, lanes = w.lanes;
     const int chunks = w.irr_chunks, irr_max = w.irr_max;
     float2* __restrict__ SK = w.sk + (size_t)sp.slot * w.slots;
@@ -1591,6 +1636,11 @@ __device__ __forceinline__ void skew_irregular_thread(const View& v, const SlotP
         }
     }
     for (int l = 0; l < L; ++l) {
+        if (ASYNC) {
+            const int need = need_nxt;
+            if (l + 1 < L) need_nxt = (int)__ldg(req + (size_t)(l + 1) * 32);
+            skew_wait(s_prog, need, lane_id, w.sync_sleep);
+        }
         // (1) block of level l + LEAD (loaded during the previous level) -> ring; start loading the next one
         if (stager) {
             s_ring[((l + SKEW_STAGE_LEAD) % SKEW_RING) * chunks + ti] = stage;
@@ -1600,7 +1650,7 @@ __device__ __forceinline__ void skew_irregular_thread(const View& v, const SlotP
         //     pull the one of level l + LEAD - 2 towards L2 / L1
         if (gatherer) {
             if (have) {
-                if (info != 0xffffffffu) val = s_xch[((l + 1) & 1) * lanes + (int)info];  // written at level l - 1
+                if (info != 0xffffffffu) val = s_xch[((l - 1) & XM) * lanes + (int)info];  // written at level l - 1
                 s_nb[ti] = val;
                 if (ti % 9 == 4) s_dd[ti / 9] = dval;
             }
@@ -1634,40 +1684,51 @@ __device__ __forceinline__ void skew_irregular_thread(const View& v, const SlotP
                 for (int q = 0; q < 9; ++q) nb[q] = s_nb[ti * 9 + q];
                 const float2 r = spiral_visit(nb, s_dd[ti]);
                 const int mirror = (int)hd[1];
-                s_xch[(l & 1) * lanes + (int)hd[2]] = r;
+                s_xch[(l & XM) * lanes + (int)hd[2]] = r;
                 SK[own] = r;
                 if (mirror >= 0) SK[mirror] = r;
                 Gn[hd[3]] = r.x;
                 if (s_dd[ti] >= 0.0f) Cn[hd[3]] = r.y;
             }
         }
-        __syncthreads();
+        if (ASYNC) {
+            skew_named_barrier();   // both warps are done with the level (and with s_nb / s_dd)
+            if (ti == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(s_prog + agent)), "r"(l + 1) : "memory");
+        } else {
+            __syncthreads();
+        }
     }
 }
 
-template <int MAXT, int MIN_CTAS = 1>
+template <int MAXT, int MIN_CTAS = 1, bool ASYNC = false>
 __global__ void __launch_bounds__(MAXT, MIN_CTAS) k_spiral_skew(View v, const SlotParams* __restrict__ batch) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const SkewView& w = v.skew;
-    // [ring: SKEW_RING levels x irr_chunks uint4][xch: 2 x lanes float2][nb: irr_max*9 float2][dd: irr_max float]
+    // [ring: SKEW_RING levels x irr_chunks uint4][xch: depth x lanes float2][nb: irr_max*9 float2][dd: irr_max float][progress: 32 int]
     uint4* s_ring = reinterpret_cast<uint4*>(s_raw);
     float2* s_xch = reinterpret_cast<float2*>(s_ring + SKEW_RING * w.irr_chunks);
-    float2* s_nb = s_xch + 2 * w.lanes;
+    float2* s_nb = s_xch + (ASYNC ? SKEW_XCH_ASYNC : 2) * w.lanes;
     float* s_dd = reinterpret_cast<float*>(s_nb + w.irr_max * 9);
+    int* s_prog = reinterpret_cast<int*>(s_dd + w.irr_max);
     const SlotParams& sp = batch[blockIdx.x];
     const int tid = threadIdx.x;
+    if (ASYNC) {
+        // agents that do not exist count as finished (their table entries are 0 anyway)
+        if (tid < 32) s_prog[tid] = tid <= 4 * w.M / 32 ? 0 : 0x7fffffff;
+        __syncthreads();
+    }
     if (tid < 4 * w.M) {
         const int side = tid / w.M;  // warp-uniform: M is a multiple of 32
         if (side == 0)
-            skew_lane_thread<0>(v, sp, s_xch);
+            skew_lane_thread<0, ASYNC>(v, sp, s_xch, s_prog);
         else if (side == 1)
-            skew_lane_thread<1>(v, sp, s_xch);
+            skew_lane_thread<1, ASYNC>(v, sp, s_xch, s_prog);
         else if (side == 2)
-            skew_lane_thread<2>(v, sp, s_xch);
+            skew_lane_thread<2, ASYNC>(v, sp, s_xch, s_prog);
         else
-            skew_lane_thread<3>(v, sp, s_xch);
+            skew_lane_thread<3, ASYNC>(v, sp, s_xch, s_prog);
     } else {
-        skew_irregular_thread(v, sp, s_xch, s_ring, s_nb, s_dd);
+        skew_irregular_thread<ASYNC>(v, sp, s_xch, s_ring, s_nb, s_dd, s_prog);
     }
 }
 
@@ -2028,24 +2089,32 @@ int launch_scan_pipeline(const View& v, const SlotParams* batch, int count, int 
             vs.skew.ph_begin = v.skew.thr_ph_begin;
             vs.skew.ph_end = v.skew.thr_ph_end;
             vs.skew.ph_cell0 = v.skew.thr_ph_cell0;
+            vs.skew.req = v.skew.thr_req;
         }
+        const bool async = vs.skew.req != nullptr;   // point-to-point synchronisation table of this thread layout
         const int threads = 4 * vs.skew.M + SKEW_IRR_THREADS;
-        const size_t shm = (size_t)SKEW_RING * v.skew.irr_chunks * sizeof(uint4) + (size_t)2 * v.skew.lanes * sizeof(float2) +
-                           (size_t)v.skew.irr_max * 9 * sizeof(float2) + (size_t)v.skew.irr_max * sizeof(float) + 16;
-        if (shm > 48 * 1024) {   // very large maps (N > ~1500): opt in to more dynamic shared memory
-            cudaFuncSetAttribute(k_spiral_skew<320, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
-            cudaFuncSetAttribute(k_spiral_skew<448, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
-            cudaFuncSetAttribute(k_spiral_skew<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
-            cudaFuncSetAttribute(k_spiral_skew<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
-        }
+        const size_t shm = (size_t)SKEW_RING * v.skew.irr_chunks * sizeof(uint4) + (size_t)(async ? SKEW_XCH_ASYNC : 2) * v.skew.lanes * sizeof(float2) +
+                           (size_t)v.skew.irr_max * 9 * sizeof(float2) + (size_t)v.skew.irr_max * sizeof(float) + 32 * sizeof(int) + 16;
+#define GG_SKEW_LAUNCH(T, C)                                                                                                     \
+    {                                                                                                                            \
+        if (shm > 48 * 1024) {   /* large maps: opt in to more dynamic shared memory */                                         \
+            cudaFuncSetAttribute(k_spiral_skew<T, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);             \
+            cudaFuncSetAttribute(k_spiral_skew<T, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);              \
+        }                                                                                                                        \
+        if (async)                                                                                                               \
+            GG_LAUNCH(K_SPIRAL, (k_spiral_skew<T, C, true><<<count, threads, shm, st>>>(vs, batch)));                            \
+        else                                                                                                                     \
+            GG_LAUNCH(K_SPIRAL, (k_spiral_skew<T, C, false><<<count, threads, shm, st>>>(vs, batch)));                           \
+    }
         if (threads <= 320)       // time-shared lane threads (GG_SPIRAL_M): several scans share an SM
-            GG_LAUNCH(K_SPIRAL, (k_spiral_skew<320, 3><<<count, threads, shm, st>>>(vs, batch)));
+            GG_SKEW_LAUNCH(320, 3)
         else if (threads <= 448)
-            GG_LAUNCH(K_SPIRAL, (k_spiral_skew<448, 2><<<count, threads, shm, st>>>(vs, batch)));
+            GG_SKEW_LAUNCH(448, 2)
         else if (threads <= 768)
-            GG_LAUNCH(K_SPIRAL, k_spiral_skew<768><<<count, threads, shm, st>>>(vs, batch));
+            GG_SKEW_LAUNCH(768, 1)
         else
-            GG_LAUNCH(K_SPIRAL, k_spiral_skew<1024><<<count, threads, shm, st>>>(vs, batch));
+            GG_SKEW_LAUNCH(1024, 1)
+#undef GG_SKEW_LAUNCH
     } else if (v.spiral_recs) {
         const size_t shm = (size_t)((v.levels + 4) & ~3) * sizeof(int) + (size_t)(v.spiral_dist + 1) * v.spiral_threads * sizeof(float2);
 #define GG_SPIRAL_CASE(T, D)                                                                      \

@@ -423,6 +423,37 @@ def test_batch_of_ten_uses_the_shared_sm_spiral_layout(dim, res):
     g.close()
 
 
+@pytest.mark.parametrize("dim,res", [(33.0, 0.33), (99.0, 0.33), (81.2, 0.4)])
+def test_spiral_point_to_point_sync_variant(monkeypatch, dim, res):
+    """GG_SPIRAL_ASYNC=1: k_spiral_skew without the CTA barrier per level (progress counters per warp, requirement table
+    from gg_host.cpp:build_skew_sync).  Both thread layouts (one scan alone, a batch of ten) against the oracle."""
+    import torch
+
+    monkeypatch.setenv("GG_SPIRAL_ASYNC", "1")
+    B = 10
+    g = capi.GroundGridB200(dim, res, n_slots=B, max_points=131072, full_layers=False)
+    scans = [synth.scan_64(synth.make_scene(seed=810 + b), ego_xy=(0.05 * b, 0.0), seed=810 + b) for b in range(B)]
+    hp = [torch.from_numpy(np.ascontiguousarray(p).view(np.uint8).copy()).pin_memory() for p, _ in scans]
+    hl = [torch.zeros(len(p), dtype=torch.uint8).pin_memory() for p, _ in scans]
+    for b in range(B):
+        g.init_map(0.05 * b, 0.0, 0.0, slot=b)
+    first = g.filter_cloud(scans[0][0], scans[0][1], 0.0, slot=0)      # one scan alone: one thread per lane
+    descs = g.make_descs(list(range(B)), [len(p) for p, _ in scans], [o for _, o in scans], [0.0] * B)
+    g.filter_cloud_batch_ptrs(descs, [t.data_ptr() for t in hp], [t.data_ptr() for t in hl])   # batch: time-shared lane threads
+    for b in range(B):
+        o = Oracle(dim, res)
+        o.init_map(0.05 * b, 0.0, 0.0)
+        if b == 0:   # slot 0 saw its cloud twice: alone, then in the batch
+            want, _, _ = o.filter_cloud(scans[0][0], scans[0][1], 0.0, threads=1)
+            assert np.array_equal(first, want)
+        want, _, _ = o.filter_cloud(scans[b][0], scans[b][1], 0.0, threads=1)
+        assert np.array_equal(hl[b].numpy(), want), f"slot {b}"
+        for name in ("ground", "groundpatch"):
+            r = diff_report(name, g.layer(name, slot=b), o.layer(name))
+            assert r is None, f"slot {b}: {r}"
+    g.close()
+
+
 @pytest.mark.parametrize("unit", ["2", "32"])
 def test_overlapped_batches_begin_wait(monkeypatch, unit):
     """gg_filter_cloud_batch_begin/_wait: the clouds of step t+1 are packed and copied while the kernels of
