@@ -832,7 +832,7 @@ int gg_create(double dimension_m, float resolution, int device, int n_slots, siz
                 *d_req = nullptr;
                 std::vector<uint16_t> rq;
                 int n_agents = 0;
-                if (!want_async || !gg::build_skew_sync(sk, m_, 4, rq, n_agents)) return GG_OK;
+                if (!want_async || !gg::build_skew_sync(sk, m_, gg::SKEW_XCH_ASYNC, rq, n_agents)) return GG_OK;
                 uint16_t* d = nullptr;
                 int rc2;
                 if ((rc2 = dev_alloc(h, &d, rq.size()))) return rc2;

@@ -75,6 +75,8 @@ struct SlotParams {
 };
 
 // Device side of the skewed-layout spiral (gg_host.h:SkewTables); null sk -> not used.
+constexpr int SKEW_XCH_ASYNC = 4;    // depth of the exchange ring of the barrier-free spiral variants (the barrier variant needs 2); the
+                                     // synchronisation table is built for exactly this depth (gg_capi.cu -> build_skew_sync)
 struct SkewView {
     float2* sk;             // [n_slots][slots] (G, C) in (side, level, ring) order
     float* sd;              // [n_slots][slots] decayed confidence the visit will store, -1: confidence unchanged

@@ -1445,7 +1445,6 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 // reached the progress the host table asks for (gg_host.cpp:build_skew_sync: exact RAW / WAR / WAW sets of the level's
 // visits).  Neighbouring rings trail each other by three levels, so most requirements leave a level of slack: a warp
 // that is late (a cache miss, a lost issue slot) no longer stalls the whole CTA.  Lane b of a warp watches agent b.
-constexpr int SKEW_XCH_ASYNC = 4;    // depth of the exchange ring of the ASYNC variants (the barrier variant needs 2)
 __device__ __forceinline__ void skew_publish(int* s_prog, int agent, int completed, int lane) {
     __syncwarp();
     if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(s_prog + agent)), "r"(completed) : "memory");
